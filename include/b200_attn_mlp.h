@@ -1,0 +1,152 @@
+/*
+ * b200_attn_mlp.h — C-ABI of the B200 (sm_100a) attention + FusedMLP hot path.
+ *
+ * This is the drop-in boundary. The reference has no FFI of its own: its seam is the Python
+ * function layer in kernels/triton/*.py. Every entry point below names the reference function it replaces
+ * (file:line under the reference tree). INTEGRATION.md shows the ctypes binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types. Returns 0 (B200_OK) or a negative error
+ *     code; b200_last_error() returns a thread-local description. Never throws, never allocates or frees
+ *     caller memory, never synchronises the device (except b200_selftest_sync helpers that say so).
+ *   - All data pointers are DEVICE pointers. Strides are in ELEMENTS. `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream).
+ *   - dtype: B200_DTYPE_BF16 or B200_DTYPE_FP16 for q/k/v/o/x/weights; statistics (LSE) and split-K partials
+ *     are fp32. Accumulation and softmax are always fp32.
+ *   - There is no CPU fallback: on a machine without an sm_100 GPU every compute call returns
+ *     B200_ERR_NO_DEVICE / B200_ERR_CUDA.
+ */
+#ifndef B200_ATTN_MLP_H_
+#define B200_ATTN_MLP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID_ARGUMENT (-1)
+#define B200_ERR_UNSUPPORTED (-2)
+#define B200_ERR_CUDA (-3)
+#define B200_ERR_NO_DEVICE (-4)
+#define B200_ERR_WORKSPACE (-5)
+
+#define B200_DTYPE_BF16 0
+#define B200_DTYPE_FP16 1
+
+/* Activation selector of the FusedMLP path.
+ *   GELU_TANH : kernels/triton/mlp_kernels.py:144-161 (Triton kernel) == kernels/mlp/fused_mlp.py:223-237
+ *   GELU_ERF  : kernels/mlp/fused_mlp.py:162-163, kernels/triton/mlp_kernels.py:783 (exact F.gelu)
+ *   RELU      : kernels/triton/mlp_kernels.py:233-414, kernels/mlp/fused_mlp.py:299-315
+ *   SWIGLU    : silu(gate) * up, kernels/triton/mlp_kernels.py:567-572, kernels/mlp/fused_mlp.py:262-275
+ *   NONE      : plain Linear (+bias), used for the down projection alone                                  */
+#define B200_ACT_NONE 0
+#define B200_ACT_GELU_TANH 1
+#define B200_ACT_GELU_ERF 2
+#define B200_ACT_RELU 3
+#define B200_ACT_SWIGLU 4
+
+/* KV-cache layouts of the decode path */
+#define B200_KV_CONTIGUOUS 0 /* [B, S_max, Hkv, D]                      baseline/inference.py:866-874   */
+#define B200_KV_PAGED 1      /* [num_blocks, L, block_size, Hkv, D]     baseline/inference.py:1077-1084 */
+
+/* ---- library / device -------------------------------------------------------------------------------- */
+const char* b200_version(void);
+const char* b200_last_error(void);
+/* 1 if the current CUDA device is compute capability 10.x, 0 if not, negative error if no device. */
+int b200_arch_ok(void);
+
+/* ---- K1: tiled online-softmax attention forward (prefill) -------------------------------------------
+ * Replaces triton_flash_attention / _flash_attention_forward_kernel
+ *   (kernels/triton/flash_attention_kernels.py:1150-1358, :38-325), the attention inside
+ *   FlashAttention3.forward (kernels/attention/flash_attention.py:145-225), and — called once per ring step —
+ *   triton_ring_attention_forward (kernels/triton/attention_kernels.py:909-998).
+ *
+ *   O[b,i,h,:] = softmax_j( scale * <Q[b,i,h,:], K[b,j,h/g,:]> + mask ) V[b,j,h/g,:],   g = Hq/Hkv
+ *   LSE[b,h,i] = log sum_j exp(scale * s_ij)          (fp32, natural log; -inf for a fully masked row, O = 0)
+ *
+ *   mask: key j is visible to query i iff  j < kv_len(b)  and (not causal or  j <= i + causal_offset).
+ *         causal_offset = (global position of query row 0) - (global position of key row 0); 0 for
+ *         self-attention prefill (reference: triu(diagonal=1), flash_attention.py:1221-1225), Sk - Sq for
+ *         bottom-right alignment, arbitrary for ring steps / chunked prefill.
+ *   kv_lens: optional int32[B] (device) per-batch key count (right-padding masks); NULL = Sk for all.
+ *
+ *   q [B,Sq,Hq,D], k/v [B,Sk,Hkv,D], o [B,Sq,Hq,D] addressed through (batch, seq, head) element strides,
+ *   D contiguous; D in {64, 128}; pointers 16-byte aligned and strides multiples of 8 elements.
+ *   lse: fp32 [B,Hq,Sq] contiguous, may be NULL.                                                          */
+int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Sq, int Sk, int Hq,
+                int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],
+                const int64_t o_strides[3], float softmax_scale, int causal, int64_t causal_offset,
+                const int32_t* kv_lens, int dtype, void* stream);
+
+/* ---- LSE merge: combine two partial attention results over disjoint key sets ---------------------------
+ * The online-softmax merge algebra of kernels/triton/attention_kernels.py:1567-1585, used by the ring
+ * (parallelism/sequence_parallel.py:519-585 rebuilt exact):
+ *   lse = logaddexp(lse_a, lse_b);  o = o_a * exp(lse_a - lse) + o_b * exp(lse_b - lse)
+ * In place on (o_acc fp32 [B,Sq,Hq,D] contiguous, lse_acc fp32 [B,Hq,Sq]); the incoming block is (o_b 16-bit
+ * with strides, lse_b fp32 [B,Hq,Sq]). A side with lse = -inf contributes nothing.                        */
+int b200_lse_merge(float* o_acc, float* lse_acc, const void* o_b, const float* lse_b, int B, int Sq, int Hq, int D,
+                   const int64_t ob_strides[3], int dtype, void* stream);
+
+/* Convert the fp32 ring accumulator to the 16-bit output tensor (strided). */
+int b200_cast_out(const float* o_acc, void* o, int B, int Sq, int Hq, int D, const int64_t o_strides[3], int dtype,
+                  void* stream);
+
+/* ---- K2: single-token decode attention against a KV cache (HBM-bound, split-K) -------------------------
+ * Replaces triton_paged_attention_forward / _paged_attention_fwd_kernel
+ *   (kernels/triton/attention_kernels.py:1206-1311, :628-808).  No causal mask, keys j < context_len(b)
+ *   (attention_kernels.py:771-777).  GQA: query head h reads kv head h / (Hq/Hkv).
+ *
+ *   q, o      : [B, Hq, D] (the reference's [B,Hq,1,D] with the unit axis dropped), contiguous
+ *   k_cache, v_cache :
+ *       B200_KV_CONTIGUOUS  [B, S_max, Hkv, D]   (kv_batch_stride / kv_token_stride in elements)
+ *       B200_KV_PAGED       [num_blocks, L, block_size, Hkv, D] contiguous, addressed through
+ *                           block_table int32 [B, max_blocks_per_seq] and layer_idx
+ *   context_lens : int32 [B] (device), number of valid keys per sequence (includes the appended token)
+ *   lse       : optional fp32 [B, Hq]
+ *   num_splits: >= 1 splits of the key axis per (batch, kv head); 0 = choose so the grid fills the SMs.
+ *   workspace : device scratch of at least b200_fa_decode_workspace_bytes(...) bytes (may be NULL when the
+ *               resolved num_splits == 1).                                                               */
+int64_t b200_fa_decode_workspace_bytes(int B, int Hq, int Hkv, int D, int max_context_len, int num_splits);
+int b200_fa_decode_num_splits(int B, int Hkv, int max_context_len);
+int b200_fa_decode(const void* q, const void* k_cache, const void* v_cache, void* o, float* lse, int B, int Hq,
+                   int Hkv, int D, const int32_t* context_lens, int max_context_len, float softmax_scale, int layout,
+                   int64_t kv_batch_stride, int64_t kv_token_stride, const int32_t* block_table,
+                   int max_blocks_per_seq, int block_size, int num_layers, int layer_idx, int num_splits,
+                   void* workspace, int64_t workspace_bytes, int dtype, void* stream);
+
+/* ---- KV append: write the new token's K,V into the cache at position context_len-1 --------------------
+ * Replaces triton_reshape_and_cache / _reshape_and_cache_kernel (attention_kernels.py:1314-1407, :811-905).
+ *   key, value: [B, Hkv, D] contiguous (the reference's [B,1,Hkv,D]).                                    */
+int b200_kv_append(const void* key, const void* value, void* k_cache, void* v_cache, int B, int Hkv, int D,
+                   const int32_t* context_lens, int layout, int64_t kv_batch_stride, int64_t kv_token_stride,
+                   const int32_t* block_table, int max_blocks_per_seq, int block_size, int num_layers,
+                   int layer_idx, int dtype, void* stream);
+
+/* ---- K3: FusedMLP ---------------------------------------------------------------------------------------
+ * Replaces triton_fused_mlp (kernels/triton/mlp_kernels.py:648-756) and FusedMLP*._forward_*
+ *   (kernels/mlp/fused_mlp.py:59-72, :159-178, :223-237, :262-275):
+ *      y = act(x W_up^T + b_up) W_down^T + b_down                        (GELU_TANH / GELU_ERF / RELU)
+ *      y = (silu(x W_gate^T + b_gate) * (x W_up^T + b_up)) W_down^T + b_down          (SWIGLU)
+ *   x [T, h] (row stride ldx), w_up / w_gate [i, h], w_down [h_out, i] in nn.Linear layout ([out, in], row
+ *   contiguous), biases [i] / [h_out] or NULL, y [T, h_out] (row stride ldy). h, i, h_out multiples of 8.
+ *   workspace: T * i elements of `dtype` for the activated intermediate (it is written once and consumed
+ *   from L2 by the down projection).                                                      */
+int64_t b200_fused_mlp_workspace_bytes(int64_t T, int h, int i);
+int b200_fused_mlp(const void* x, int64_t ldx, const void* w_up, const void* b_up, const void* w_gate,
+                   const void* b_gate, const void* w_down, const void* b_down, void* y, int64_t ldy, int64_t T,
+                   int h, int i, int h_out, int act, void* workspace, int64_t workspace_bytes, int dtype,
+                   void* stream);
+
+/* One tcgen05 GEMM with a fused epilogue: y = act(x W^T + b) (or the SwiGLU pair form when w_gate != NULL).
+ * This is ColumnParallelLinear/RowParallelLinear's F.linear (parallelism/tensor_parallel.py:173, :299) and
+ * the building block of b200_fused_mlp. x [T,K] (ldx), w [N,K], y [T,N] (ldy).                          */
+int b200_linear_act(const void* x, int64_t ldx, const void* w, const void* b, const void* w_gate,
+                    const void* b_gate, void* y, int64_t ldy, int64_t T, int K, int N, int act, int dtype,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_ATTN_MLP_H_ */

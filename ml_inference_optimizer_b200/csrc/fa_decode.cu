@@ -1,0 +1,543 @@
+// K2 — single-token decode attention against a KV cache for sm_100a, plus the small bandwidth-bound helpers
+// of the path (split-K reduce, KV append, LSE merge for the ring, fp32 -> 16-bit cast).
+//
+// Replaces _paged_attention_fwd_kernel / triton_paged_attention_forward
+// (kernels/triton/attention_kernels.py:628-808, :1206-1311) and _reshape_and_cache_kernel (:811-905).
+//
+// Decode attention has ~1 FLOP per KV byte (MHA), so it is an HBM-streaming kernel, not a tensor-core one:
+//   * each KV row (D 16-bit values) is read exactly once with 128-bit ld.global.nc.L1::no_allocate loads,
+//     fully coalesced (D/8 lanes cover a row, a warp instruction covers 32/(D/8) consecutive rows);
+//   * every warp keeps 16 independent 16-byte loads in flight per lane (8 K + 8 V); 8 warps per CTA and 2-3
+//     CTAs per SM give > 128 KB in flight per SM;
+//   * flash-decoding split-K: grid = (splits, Hkv, B); per-split partial (O, LSE) are merged by a tiny reduce
+//     kernel, so all 148 SMs stream even for small B*Hkv;
+//   * GQA: one CTA serves the G = Hq/Hkv query heads that share a KV head, so K/V bytes are read once per group.
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace b200 {
+namespace decode {
+
+constexpr int NUM_WARPS = 8;
+constexpr int NUM_THREADS = NUM_WARPS * 32;
+constexpr int NLOAD = 8;  // 16-byte loads in flight per lane for K (and again for V)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+struct Params {
+  const void* q;        // [B, Hq, D]
+  const void* k_cache;
+  const void* v_cache;
+  void* o;              // [B, Hq, D]
+  float* lse;           // [B, Hq] or null
+  float* part_o;        // [B, Hq, splits, D] fp32 (normalised partial outputs)
+  float* part_lse;      // [B, Hq, splits]
+  const int32_t* context_lens;
+  const int32_t* block_table;
+  int B, Hq, Hkv;
+  int splits;
+  float scale_log2;     // softmax_scale * log2(e)
+  int64_t kv_batch_stride, kv_token_stride;  // contiguous layout, elements
+  int max_blocks_per_seq, block_size, num_layers, layer_idx;
+};
+
+template <int D, int G, typename T, bool PAGED>
+__global__ void __launch_bounds__(NUM_THREADS)
+decode_kernel(const Params p) {
+  constexpr int LPR = D / 8;          // lanes per KV row
+  constexpr int RPW = 32 / LPR;       // rows per warp-wide load
+  constexpr int TILE = NLOAD * RPW;   // keys per warp iteration
+
+  const int split = blockIdx.x;
+  const int kvh = blockIdx.y;
+  const int b = blockIdx.z;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;         // which 8-element slice of the row
+  const int rsel = lane / LPR;        // which row of the warp-wide load
+
+  const int ctx = p.context_lens[b];
+  // per-batch split range, aligned to TILE
+  int chunk = (ctx + p.splits - 1) / p.splits;
+  chunk = ((chunk + TILE - 1) / TILE) * TILE;
+  const int k_begin = min(split * chunk, ctx);
+  const int k_end = min(k_begin + chunk, ctx);
+
+  // query slices (pre-scaled by softmax_scale * log2 e)
+  float qf[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const T* qp = reinterpret_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.Hq + kvh * G + g) * D + sub * 8;
+    uint4 raw = *reinterpret_cast<const uint4*>(qp);
+    float2 f;
+    f = Pack2<T>::unpack(raw.x); qf[g][0] = f.x * p.scale_log2; qf[g][1] = f.y * p.scale_log2;
+    f = Pack2<T>::unpack(raw.y); qf[g][2] = f.x * p.scale_log2; qf[g][3] = f.y * p.scale_log2;
+    f = Pack2<T>::unpack(raw.z); qf[g][4] = f.x * p.scale_log2; qf[g][5] = f.y * p.scale_log2;
+    f = Pack2<T>::unpack(raw.w); qf[g][6] = f.x * p.scale_log2; qf[g][7] = f.y * p.scale_log2;
+  }
+
+  float m_run[G], l_run[G], acc[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m_run[g] = -INFINITY;
+    l_run[g] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
+  }
+
+  const T* kc = reinterpret_cast<const T*>(p.k_cache);
+  const T* vc = reinterpret_cast<const T*>(p.v_cache);
+  const int32_t* bt = PAGED ? p.block_table + static_cast<int64_t>(b) * p.max_blocks_per_seq : nullptr;
+  const bool bs_pow2 = PAGED && ((p.block_size & (p.block_size - 1)) == 0);
+  const int bs_shift = bs_pow2 ? (31 - __clz(p.block_size)) : 0;
+
+  for (int t0 = k_begin + warp * TILE; t0 < k_end; t0 += NUM_WARPS * TILE) {
+    uint4 kraw[NLOAD], vraw[NLOAD];
+    bool valid[NLOAD];
+    // ---- issue all loads of the tile ----
+#pragma unroll
+    for (int i = 0; i < NLOAD; ++i) {
+      const int key = t0 + i * RPW + rsel;
+      valid[i] = key < k_end;
+      int64_t off;
+      if constexpr (PAGED) {
+        int blk = 0, in_blk = 0;
+        if (valid[i]) {
+          const int bi = bs_pow2 ? (key >> bs_shift) : (key / p.block_size);
+          in_blk = bs_pow2 ? (key & (p.block_size - 1)) : (key - bi * p.block_size);
+          blk = bt[bi];
+        }
+        off = ((static_cast<int64_t>(blk) * p.num_layers + p.layer_idx) * p.block_size + in_blk) *
+                  (static_cast<int64_t>(p.Hkv) * D) +
+              kvh * D + sub * 8;
+      } else {
+        off = static_cast<int64_t>(b) * p.kv_batch_stride + static_cast<int64_t>(key) * p.kv_token_stride +
+              kvh * D + sub * 8;
+      }
+      if (valid[i]) {
+        kraw[i] = ld_stream(kc + off);
+        vraw[i] = ld_stream(vc + off);
+      } else {
+        kraw[i] = make_uint4(0, 0, 0, 0);
+        vraw[i] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    // ---- scores ----
+    float s[G][NLOAD];
+#pragma unroll
+    for (int i = 0; i < NLOAD; ++i) {
+      float kf[8];
+      float2 f;
+      f = Pack2<T>::unpack(kraw[i].x); kf[0] = f.x; kf[1] = f.y;
+      f = Pack2<T>::unpack(kraw[i].y); kf[2] = f.x; kf[3] = f.y;
+      f = Pack2<T>::unpack(kraw[i].z); kf[4] = f.x; kf[5] = f.y;
+      f = Pack2<T>::unpack(kraw[i].w); kf[6] = f.x; kf[7] = f.y;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float d = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d = fmaf(qf[g][e], kf[e], d);
+#pragma unroll
+        for (int x = LPR / 2; x >= 1; x >>= 1) d += __shfl_xor_sync(0xffffffffu, d, x);
+        s[g][i] = valid[i] ? d : -INFINITY;
+      }
+    }
+    // ---- online softmax update (one rescale per tile) ----
+    float pr[G][NLOAD];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float tmax = s[g][0];
+#pragma unroll
+      for (int i = 1; i < NLOAD; ++i) tmax = fmaxf(tmax, s[g][i]);
+#pragma unroll
+      for (int x = LPR; x < 32; x <<= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, x));
+      const float m_new = fmaxf(m_run[g], tmax);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = fast_exp2(m_run[g] - m_safe);  // m_run = -inf -> 0
+      m_run[g] = m_new;
+      l_run[g] *= corr;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[g][e] *= corr;
+#pragma unroll
+      for (int i = 0; i < NLOAD; ++i) {
+        pr[g][i] = fast_exp2(s[g][i] - m_safe);
+        l_run[g] += pr[g][i];
+      }
+    }
+    // ---- P V ----
+#pragma unroll
+    for (int i = 0; i < NLOAD; ++i) {
+      float vf[8];
+      float2 f;
+      f = Pack2<T>::unpack(vraw[i].x); vf[0] = f.x; vf[1] = f.y;
+      f = Pack2<T>::unpack(vraw[i].y); vf[2] = f.x; vf[3] = f.y;
+      f = Pack2<T>::unpack(vraw[i].z); vf[4] = f.x; vf[5] = f.y;
+      f = Pack2<T>::unpack(vraw[i].w); vf[6] = f.x; vf[7] = f.y;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(pr[g][i], vf[e], acc[g][e]);
+      }
+    }
+  }
+
+  // ---- combine the row groups of a warp (they share m_run) ----
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int x = LPR; x < 32; x <<= 1) {
+      l_run[g] += __shfl_xor_sync(0xffffffffu, l_run[g], x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[g][e] += __shfl_xor_sync(0xffffffffu, acc[g][e], x);
+    }
+  }
+
+  // ---- combine the warps of the CTA through shared memory ----
+  __shared__ float sm_m[NUM_WARPS][G];
+  __shared__ float sm_l[NUM_WARPS][G];
+  __shared__ float sm_acc[NUM_WARPS][G][D];
+  if (rsel == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sm_acc[warp][g][sub * 8 + e] = acc[g][e];
+      if (sub == 0) {
+        sm_m[warp][g] = m_run[g];
+        sm_l[warp][g] = l_run[g];
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int idx = threadIdx.x; idx < G * D; idx += NUM_THREADS) {
+    const int g = idx / D;
+    const int d = idx - g * D;
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NUM_WARPS; ++w) m = fmaxf(m, sm_m[w][g]);
+    const float m_safe = (m == -INFINITY) ? 0.f : m;
+    float l = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < NUM_WARPS; ++w) {
+      const float c = fast_exp2(sm_m[w][g] - m_safe);
+      l = fmaf(sm_l[w][g], c, l);
+      o = fmaf(sm_acc[w][g][d], c, o);
+    }
+    const float inv_l = l > 0.f ? 1.0f / l : 0.f;
+    const float out = o * inv_l;
+    const float lse = l > 0.f ? (m + log2f(l)) * kLn2 : -INFINITY;
+    const int h = kvh * G + g;
+    if (p.splits == 1) {
+      T* op = reinterpret_cast<T*>(p.o) + (static_cast<int64_t>(b) * p.Hq + h) * D + d;
+      if constexpr (Pack2<T>::kIsBf16) *op = __float2bfloat16_rn(out);
+      else *op = __float2half_rn(out);
+      if (d == 0 && p.lse != nullptr) p.lse[static_cast<int64_t>(b) * p.Hq + h] = lse;
+    } else {
+      const int64_t row = (static_cast<int64_t>(b) * p.Hq + h) * p.splits + split;
+      p.part_o[row * D + d] = out;
+      if (d == 0) p.part_lse[row] = lse;
+    }
+  }
+}
+
+// merge the per-split partials: o = sum_s exp(lse_s - lse) o_s
+template <int D, typename T>
+__global__ void decode_reduce_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
+                                     void* __restrict__ o, float* __restrict__ lse, int splits) {
+  const int64_t row = blockIdx.x;  // b * Hq + h
+  const int d = threadIdx.x;
+  float m = -INFINITY;
+  for (int s = 0; s < splits; ++s) m = fmaxf(m, part_lse[row * splits + s]);
+  const float m_safe = (m == -INFINITY) ? 0.f : m;
+  float l = 0.f, acc = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float w = __expf(part_lse[row * splits + s] - m_safe);
+    l += w;
+    acc = fmaf(w, part_o[(row * splits + s) * D + d], acc);
+  }
+  const float out = l > 0.f ? acc / l : 0.f;
+  T* op = reinterpret_cast<T*>(o) + row * D + d;
+  if constexpr (Pack2<T>::kIsBf16) *op = __float2bfloat16_rn(out);
+  else *op = __float2half_rn(out);
+  if (d == 0 && lse != nullptr) lse[row] = l > 0.f ? m + __logf(l) : -INFINITY;
+}
+
+template <typename T>
+__global__ void kv_append_kernel(const T* __restrict__ key, const T* __restrict__ value, T* __restrict__ k_cache,
+                                 T* __restrict__ v_cache, const int32_t* __restrict__ context_lens, int row_elems,
+                                 int layout, int64_t kv_batch_stride, int64_t kv_token_stride,
+                                 const int32_t* __restrict__ block_table, int max_blocks_per_seq, int block_size,
+                                 int num_layers, int layer_idx) {
+  const int b = blockIdx.x;
+  const int pos = context_lens[b] - 1;  // the appended token is the last valid one (attention_kernels.py:862-866)
+  if (pos < 0) return;
+  int64_t base;
+  if (layout == B200_KV_PAGED) {
+    const int bi = pos / block_size;
+    const int in_blk = pos - bi * block_size;
+    const int blk = block_table[static_cast<int64_t>(b) * max_blocks_per_seq + bi];
+    base = ((static_cast<int64_t>(blk) * num_layers + layer_idx) * block_size + in_blk) * row_elems;
+  } else {
+    base = static_cast<int64_t>(b) * kv_batch_stride + static_cast<int64_t>(pos) * kv_token_stride;
+  }
+  const uint4* ks = reinterpret_cast<const uint4*>(key + static_cast<int64_t>(b) * row_elems);
+  const uint4* vs = reinterpret_cast<const uint4*>(value + static_cast<int64_t>(b) * row_elems);
+  uint4* kd = reinterpret_cast<uint4*>(k_cache + base);
+  uint4* vd = reinterpret_cast<uint4*>(v_cache + base);
+  for (int i = threadIdx.x; i < row_elems / 8; i += blockDim.x) {
+    kd[i] = ks[i];
+    vd[i] = vs[i];
+  }
+}
+
+// in-place LSE merge of an incoming (o_b, lse_b) block into the fp32 ring accumulator
+template <typename T>
+__global__ void lse_merge_kernel(float* __restrict__ o_acc, float* __restrict__ lse_acc, const T* __restrict__ o_b,
+                                 const float* __restrict__ lse_b, int B, int Sq, int Hq, int D, int64_t sb, int64_t ss,
+                                 int64_t sh) {
+  // one thread per 8 output elements; threads of a (b, s, h) row are adjacent
+  const int vec_per_row = D / 8;
+  const int64_t total = static_cast<int64_t>(B) * Sq * Hq * vec_per_row;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % vec_per_row);
+  const int64_t row = idx / vec_per_row;  // (b * Sq + s) * Hq + h
+  const int h = static_cast<int>(row % Hq);
+  const int64_t bs_ = row / Hq;
+  const int s = static_cast<int>(bs_ % Sq);
+  const int b = static_cast<int>(bs_ / Sq);
+  const int64_t li = (static_cast<int64_t>(b) * Hq + h) * Sq + s;
+  const float la = lse_acc[li];
+  const float lb = lse_b[li];
+  const float m = fmaxf(la, lb);
+  float wa, wb, lnew;
+  if (m == -INFINITY) {
+    wa = 0.f; wb = 0.f; lnew = -INFINITY;
+  } else {
+    const float ea = __expf(la - m), eb = __expf(lb - m);
+    const float sum = ea + eb;
+    wa = ea / sum; wb = eb / sum;
+    lnew = m + __logf(sum);
+  }
+  float* oa = o_acc + row * D + v * 8;
+  const T* ob = o_b + static_cast<int64_t>(b) * sb + static_cast<int64_t>(s) * ss + static_cast<int64_t>(h) * sh + v * 8;
+  const uint4 raw = *reinterpret_cast<const uint4*>(ob);
+  float4 a0 = *reinterpret_cast<float4*>(oa);
+  float4 a1 = *reinterpret_cast<float4*>(oa + 4);
+  float2 f;
+  f = Pack2<T>::unpack(raw.x); a0.x = a0.x * wa + f.x * wb; a0.y = a0.y * wa + f.y * wb;
+  f = Pack2<T>::unpack(raw.y); a0.z = a0.z * wa + f.x * wb; a0.w = a0.w * wa + f.y * wb;
+  f = Pack2<T>::unpack(raw.z); a1.x = a1.x * wa + f.x * wb; a1.y = a1.y * wa + f.y * wb;
+  f = Pack2<T>::unpack(raw.w); a1.z = a1.z * wa + f.x * wb; a1.w = a1.w * wa + f.y * wb;
+  *reinterpret_cast<float4*>(oa) = a0;
+  *reinterpret_cast<float4*>(oa + 4) = a1;
+  __syncwarp();
+  if (v == 0) lse_acc[li] = lnew;
+}
+
+template <typename T>
+__global__ void cast_out_kernel(const float* __restrict__ o_acc, T* __restrict__ o, int B, int Sq, int Hq, int D,
+                                int64_t sb, int64_t ss, int64_t sh) {
+  const int vec_per_row = D / 8;
+  const int64_t total = static_cast<int64_t>(B) * Sq * Hq * vec_per_row;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % vec_per_row);
+  const int64_t row = idx / vec_per_row;
+  const int h = static_cast<int>(row % Hq);
+  const int64_t bs_ = row / Hq;
+  const int s = static_cast<int>(bs_ % Sq);
+  const int b = static_cast<int>(bs_ / Sq);
+  const float4 a0 = *reinterpret_cast<const float4*>(o_acc + row * D + v * 8);
+  const float4 a1 = *reinterpret_cast<const float4*>(o_acc + row * D + v * 8 + 4);
+  uint4 pk;
+  pk.x = Pack2<T>::pack(a0.x, a0.y);
+  pk.y = Pack2<T>::pack(a0.z, a0.w);
+  pk.z = Pack2<T>::pack(a1.x, a1.y);
+  pk.w = Pack2<T>::pack(a1.z, a1.w);
+  T* op = o + static_cast<int64_t>(b) * sb + static_cast<int64_t>(s) * ss + static_cast<int64_t>(h) * sh + v * 8;
+  *reinterpret_cast<uint4*>(op) = pk;
+}
+
+template <int D, int G, typename T>
+int launch_decode(const Params& p, bool paged, cudaStream_t stream) {
+  dim3 grid(p.splits, p.Hkv, p.B);
+  if (paged) decode_kernel<D, G, T, true><<<grid, NUM_THREADS, 0, stream>>>(p);
+  else decode_kernel<D, G, T, false><<<grid, NUM_THREADS, 0, stream>>>(p);
+  B200_CUDA_OK(cudaGetLastError());
+  if (p.splits > 1) {
+    decode_reduce_kernel<D, T><<<p.B * p.Hq, D, 0, stream>>>(p.part_o, p.part_lse, p.o, p.lse, p.splits);
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+template <int D, typename T>
+int dispatch_group(int G, const Params& p, bool paged, cudaStream_t stream) {
+  switch (G) {
+    case 1: return launch_decode<D, 1, T>(p, paged, stream);
+    case 2: return launch_decode<D, 2, T>(p, paged, stream);
+    case 4: return launch_decode<D, 4, T>(p, paged, stream);
+    case 8: return launch_decode<D, 8, T>(p, paged, stream);
+    default:
+      return set_error(B200_ERR_UNSUPPORTED, "decode: Hq/Hkv = %d is not supported (1, 2, 4, 8)", G);
+  }
+}
+
+}  // namespace decode
+}  // namespace b200
+
+extern "C" {
+
+int b200_fa_decode_num_splits(int B, int Hkv, int max_context_len) {
+  if (B <= 0 || Hkv <= 0 || max_context_len <= 0) return 1;
+  const int sms = b200::sm_count();
+  const int64_t ctas = static_cast<int64_t>(B) * Hkv;
+  const int64_t target = 3LL * sms;  // ~3 resident CTAs per SM
+  int splits = static_cast<int>((target + ctas - 1) / ctas);
+  const int max_by_len = (max_context_len + 255) / 256;  // keep >= 256 keys per split
+  if (splits > max_by_len) splits = max_by_len;
+  if (splits < 1) splits = 1;
+  if (splits > 128) splits = 128;
+  return splits;
+}
+
+int64_t b200_fa_decode_workspace_bytes(int B, int Hq, int Hkv, int D, int max_context_len, int num_splits) {
+  int splits = num_splits > 0 ? num_splits : b200_fa_decode_num_splits(B, Hkv, max_context_len);
+  if (splits <= 1) return 0;
+  return static_cast<int64_t>(B) * Hq * splits * (D + 1) * static_cast<int64_t>(sizeof(float));
+}
+
+int b200_fa_decode(const void* q, const void* k_cache, const void* v_cache, void* o, float* lse, int B, int Hq, int Hkv,
+                   int D, const int32_t* context_lens, int max_context_len, float softmax_scale, int layout,
+                   int64_t kv_batch_stride, int64_t kv_token_stride, const int32_t* block_table,
+                   int max_blocks_per_seq, int block_size, int num_layers, int layer_idx, int num_splits,
+                   void* workspace, int64_t workspace_bytes, int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(q && k_cache && v_cache && o && context_lens, "decode: NULL pointer argument");
+  B200_CHECK_ARG(B > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "decode: bad B/Hq/Hkv = %d/%d/%d", B, Hq, Hkv);
+  B200_CHECK_ARG(D == 64 || D == 128, "decode: head_dim %d unsupported (64, 128)", D);
+  B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "decode: dtype must be bf16 or fp16");
+  B200_CHECK_ARG(layout == B200_KV_CONTIGUOUS || layout == B200_KV_PAGED, "decode: unknown KV layout %d", layout);
+  B200_CHECK_ARG(max_context_len > 0, "decode: max_context_len must be positive");
+  B200_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0 &&
+                     ((uintptr_t)o & 15) == 0,
+                 "decode: pointers must be 16-byte aligned");
+  if (layout == B200_KV_PAGED) {
+    B200_CHECK_ARG(block_table != nullptr && block_size > 0 && max_blocks_per_seq > 0 && num_layers > 0 &&
+                       layer_idx >= 0 && layer_idx < num_layers,
+                   "decode: bad paged-cache arguments");
+  } else {
+    B200_CHECK_ARG(kv_token_stride >= static_cast<int64_t>(Hkv) * D && kv_token_stride % 8 == 0 &&
+                       kv_batch_stride % 8 == 0,
+                   "decode: bad contiguous-cache strides");
+  }
+  int splits = num_splits > 0 ? num_splits : b200_fa_decode_num_splits(B, Hkv, max_context_len);
+  decode::Params p;
+  p.q = q; p.k_cache = k_cache; p.v_cache = v_cache; p.o = o; p.lse = lse;
+  p.part_o = nullptr; p.part_lse = nullptr;
+  if (splits > 1) {
+    const int64_t need = b200_fa_decode_workspace_bytes(B, Hq, Hkv, D, max_context_len, splits);
+    if (workspace == nullptr || workspace_bytes < need)
+      return set_error(B200_ERR_WORKSPACE, "decode workspace too small: need %lld bytes, got %lld", (long long)need,
+                       (long long)workspace_bytes);
+    p.part_o = static_cast<float*>(workspace);
+    p.part_lse = p.part_o + static_cast<int64_t>(B) * Hq * splits * D;
+  }
+  p.context_lens = context_lens; p.block_table = block_table;
+  p.B = B; p.Hq = Hq; p.Hkv = Hkv; p.splits = splits;
+  p.scale_log2 = softmax_scale * decode::kLog2e;
+  p.kv_batch_stride = kv_batch_stride; p.kv_token_stride = kv_token_stride;
+  p.max_blocks_per_seq = max_blocks_per_seq; p.block_size = block_size; p.num_layers = num_layers;
+  p.layer_idx = layer_idx;
+  const int G = Hq / Hkv;
+  const bool paged = layout == B200_KV_PAGED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (D == 128) {
+    return dtype == B200_DTYPE_BF16 ? decode::dispatch_group<128, __nv_bfloat16>(G, p, paged, s)
+                                    : decode::dispatch_group<128, __half>(G, p, paged, s);
+  }
+  return dtype == B200_DTYPE_BF16 ? decode::dispatch_group<64, __nv_bfloat16>(G, p, paged, s)
+                                  : decode::dispatch_group<64, __half>(G, p, paged, s);
+}
+
+int b200_kv_append(const void* key, const void* value, void* k_cache, void* v_cache, int B, int Hkv, int D,
+                   const int32_t* context_lens, int layout, int64_t kv_batch_stride, int64_t kv_token_stride,
+                   const int32_t* block_table, int max_blocks_per_seq, int block_size, int num_layers, int layer_idx,
+                   int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(key && value && k_cache && v_cache && context_lens, "kv_append: NULL pointer argument");
+  B200_CHECK_ARG(B > 0 && Hkv > 0 && D > 0 && (Hkv * D) % 8 == 0, "kv_append: bad sizes");
+  B200_CHECK_ARG(layout == B200_KV_CONTIGUOUS || layout == B200_KV_PAGED, "kv_append: unknown KV layout %d", layout);
+  if (layout == B200_KV_PAGED)
+    B200_CHECK_ARG(block_table != nullptr && block_size > 0 && max_blocks_per_seq > 0 && num_layers > 0 &&
+                       layer_idx >= 0 && layer_idx < num_layers,
+                   "kv_append: bad paged-cache arguments");
+  (void)dtype;  // a 16-bit copy: the element type does not matter
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  decode::kv_append_kernel<uint16_t><<<B, 128, 0, s>>>(
+      static_cast<const uint16_t*>(key), static_cast<const uint16_t*>(value), static_cast<uint16_t*>(k_cache),
+      static_cast<uint16_t*>(v_cache), context_lens, Hkv * D, layout, kv_batch_stride, kv_token_stride, block_table,
+      max_blocks_per_seq, block_size, num_layers, layer_idx);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_lse_merge(float* o_acc, float* lse_acc, const void* o_b, const float* lse_b, int B, int Sq, int Hq, int D,
+                   const int64_t ob_strides[3], int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(o_acc && lse_acc && o_b && lse_b && ob_strides, "lse_merge: NULL pointer argument");
+  B200_CHECK_ARG(B > 0 && Sq > 0 && Hq > 0 && D > 0 && D % 8 == 0, "lse_merge: bad sizes");
+  B200_CHECK_ARG(ob_strides[0] % 8 == 0 && ob_strides[1] % 8 == 0 && ob_strides[2] % 8 == 0 &&
+                     ((uintptr_t)o_b & 15) == 0 && ((uintptr_t)o_acc & 15) == 0,
+                 "lse_merge: o_b strides must be multiples of 8 elements and pointers 16-byte aligned");
+  B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "lse_merge: dtype must be bf16 or fp16");
+  const int64_t total = static_cast<int64_t>(B) * Sq * Hq * (D / 8);
+  const int threads = 256;
+  const int64_t blocks = (total + threads - 1) / threads;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_DTYPE_BF16)
+    decode::lse_merge_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+        o_acc, lse_acc, static_cast<const __nv_bfloat16*>(o_b), lse_b, B, Sq, Hq, D, ob_strides[0], ob_strides[1],
+        ob_strides[2]);
+  else
+    decode::lse_merge_kernel<__half><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+        o_acc, lse_acc, static_cast<const __half*>(o_b), lse_b, B, Sq, Hq, D, ob_strides[0], ob_strides[1],
+        ob_strides[2]);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+int b200_cast_out(const float* o_acc, void* o, int B, int Sq, int Hq, int D, const int64_t o_strides[3], int dtype,
+                  void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(o_acc && o && o_strides, "cast_out: NULL pointer argument");
+  B200_CHECK_ARG(B > 0 && Sq > 0 && Hq > 0 && D > 0 && D % 8 == 0, "cast_out: bad sizes");
+  B200_CHECK_ARG(o_strides[0] % 8 == 0 && o_strides[1] % 8 == 0 && o_strides[2] % 8 == 0 && ((uintptr_t)o & 15) == 0,
+                 "cast_out: strides must be multiples of 8 elements and o 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * Sq * Hq * (D / 8);
+  const int threads = 256;
+  const int64_t blocks = (total + threads - 1) / threads;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == B200_DTYPE_BF16)
+    decode::cast_out_kernel<__nv_bfloat16><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+        o_acc, static_cast<__nv_bfloat16*>(o), B, Sq, Hq, D, o_strides[0], o_strides[1], o_strides[2]);
+  else if (dtype == B200_DTYPE_FP16)
+    decode::cast_out_kernel<__half><<<static_cast<unsigned>(blocks), threads, 0, s>>>(
+        o_acc, static_cast<__half*>(o), B, Sq, Hq, D, o_strides[0], o_strides[1], o_strides[2]);
+  else
+    return set_error(B200_ERR_INVALID_ARGUMENT, "cast_out: dtype must be bf16 or fp16");
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// K1 — tiled online-softmax attention forward (prefill) for sm_100a.
+//
+// Replaces _flash_attention_forward_kernel / triton_flash_attention
+// (kernels/triton/flash_attention_kernels.py:38-325, :1150-1358) and, per ring step,
+// triton_ring_attention_forward (kernels/triton/attention_kernels.py:909-998).
+//
+// One CTA owns two 128-row query tiles of one (batch, head) and walks the KV sequence in 128-key tiles:
+//   warp 0      TMA producer   : Q tiles once, then K(j), V(j) through an mbarrier ring (128-byte swizzle)
+//   warp 1      MMA issuer     : S_t = Q_t K^T  (tcgen05.mma SS, 128x128xD, fp32 accumulators in TMEM)
+//                                O_t += P_t V   (tcgen05.mma TS: P read from TMEM, V MN-major from smem)
+//   warp 2      TMEM allocator : 512 columns = [S0 | S1 | O0 | O1]; P_t (16-bit) overlays the upper half of S_t
+//   warps 4-7   softmax of tile 0, warps 8-11 softmax of tile 1: one thread per query row — tcgen05.ld the
+//               row of S, running max / sum in fp32 registers (no shuffles), exp2 with the scale folded in,
+//               P written back to TMEM with tcgen05.st, lazy O rescale (only when the row max grew by > 2^8),
+//               final O / l -> 16-bit -> swizzled smem -> TMA store, LSE -> global.
+// The two query tiles ping-pong: while the softmax warps of tile 0 work on S_0(j+1), the tensor core runs
+// P_1(j) V(j) and Q_1 K(j+1)^T. Causal tiles above the diagonal are never loaded or computed.
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace b200 {
+namespace fa {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 128;
+constexpr int NUM_THREADS = 384;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, safe for bf16/fp16 P and fp32 sums
+
+template <int D>
+struct Cfg {
+  static constexpr int TILE_BYTES = 128 * D * 2;            // one Q / K / V tile
+  static constexpr int BOXES = D / 64;                      // 64-column (128-byte) TMA boxes per tile
+  static constexpr int KV_STAGES = (D == 128) ? 4 : 6;
+  static constexpr int SMEM_Q_OFF = 0;
+  static constexpr int SMEM_KV_OFF = 2 * TILE_BYTES;
+  static constexpr int SMEM_BAR_OFF = SMEM_KV_OFF + KV_STAGES * TILE_BYTES;
+  static constexpr int SMEM_BYTES = SMEM_BAR_OFF + 512 + 1024;
+  static constexpr uint32_t TMEM_S = 0;      // + t * 128
+  static constexpr uint32_t TMEM_P_OFF = 64; // inside the S region
+  static constexpr uint32_t TMEM_O = 256;    // + t * D
+};
+
+struct Params {
+  float* lse;               // [B, Hq, Sq] or nullptr
+  const int32_t* kv_lens;   // [B] or nullptr
+  int B, Sq, Sk, Hq, Hkv;
+  float scale_log2;         // softmax_scale * log2(e)
+  int causal;
+  int64_t causal_offset;    // key j visible to query i iff j <= i + causal_offset
+  int num_pairs;            // ceil(Sq / 256)
+};
+
+// number of KV tiles a query tile [row0, row0+128) needs
+__device__ __forceinline__ int num_kv_tiles(const Params& p, int row0, int kv_len) {
+  if (row0 >= p.Sq) return 0;
+  int64_t visible = kv_len;
+  if (p.causal) {
+    const int last_row = min(row0 + BLOCK_M - 1, p.Sq - 1);
+    const int64_t lim = static_cast<int64_t>(last_row) + p.causal_offset + 1;
+    if (lim < visible) visible = lim;
+  }
+  if (visible <= 0) return 0;
+  return static_cast<int>((visible + BLOCK_N - 1) / BLOCK_N);
+}
+
+template <int D, typename T>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const Params p) {
+  using C = Cfg<D>;
+  constexpr int NS = C::KV_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR_OFF);  // [2]
+  uint64_t* kv_full = q_full + 2;                                          // [NS]
+  uint64_t* kv_empty = kv_full + NS;                                       // [NS]
+  uint64_t* s_full = kv_empty + NS;                                        // [2]  MMA -> softmax
+  uint64_t* p_full = s_full + 2;                                           // [2]  softmax -> MMA (128 arrivals)
+  uint64_t* pv_done = p_full + 2;                                          // [2]  MMA -> softmax (O_t updated)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // heavy (late) query tiles first under a causal mask
+  const int pair = p.causal ? (p.num_pairs - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int kv_head = head / (p.Hq / p.Hkv);
+  const int q_row0 = pair * 2 * BLOCK_M;
+  int kv_len = p.Sk;
+  if (p.kv_lens != nullptr) kv_len = max(0, min(p.Sk, p.kv_lens[batch]));
+  const int n0 = num_kv_tiles(p, q_row0, kv_len);
+  const int n1 = num_kv_tiles(p, q_row0 + BLOCK_M, kv_len);
+  const int n_max = max(n0, n1);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    tma_prefetch_desc(&tmap_o);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // register budget: 384 threads x 168 at launch; the producer warpgroup gives 112 per thread to the softmax
+  // warpgroups (128 x 56 + 256 x 224 = 64512)
+  if (warp_idx < 4) {
+    setmaxnreg_dec<56>();
+  }
+  if (warp_idx == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      for (int t = 0; t < 2; ++t) {
+        if (q_row0 + t * BLOCK_M < p.Sq) {
+          mbar_arrive_expect_tx(&q_full[t], C::TILE_BYTES);
+          uint8_t* sq = smem + C::SMEM_Q_OFF + t * C::TILE_BYTES;
+#pragma unroll
+          for (int c = 0; c < C::BOXES; ++c)
+            tma_load_4d(sq + c * 16384, &tmap_q, &q_full[t], c * 64, head, q_row0 + t * BLOCK_M, batch);
+        }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_max; ++j) {
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {  // 0: K(j), 1: V(j)
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&kv_full[stage], C::TILE_BYTES);
+          uint8_t* dst = smem + C::SMEM_KV_OFF + stage * C::TILE_BYTES;
+          const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
+#pragma unroll
+          for (int c = 0; c < C::BOXES; ++c)
+            tma_load_4d(dst + c * 16384, tm, &kv_full[stage], c * 64, kv_head, j * BLOCK_N, batch);
+          if (++stage == NS) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0 && n_max > 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(BLOCK_M, BLOCK_N, Pack2<T>::kIsBf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(BLOCK_M, D, Pack2<T>::kIsBf16, false, true);
+      const uint32_t sq_addr = smem_u32(smem + C::SMEM_Q_OFF);
+      const uint32_t skv_addr = smem_u32(smem + C::SMEM_KV_OFF);
+      const int nt[2] = {n0, n1};
+
+      auto issue_qk = [&](int t, int k_stage) {
+        const uint32_t qa = sq_addr + t * C::TILE_BYTES;
+        const uint32_t ka = skv_addr + k_stage * C::TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128);
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(ka + off, 16, 1024),
+                  idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int v_stage, bool accumulate) {
+        const uint32_t va = skv_addr + v_stage * C::TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + C::TMEM_O + static_cast<uint32_t>(t * D);
+        const uint32_t p_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128) + C::TMEM_P_OFF;
+#pragma unroll
+        for (int ks = 0; ks < BLOCK_N / 16; ++ks) {
+          umma_ts(d_tmem, p_tmem + ks * 8, make_smem_desc_sw128(va + ks * 2048, 16384, 1024), idesc_pv,
+                  (accumulate || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[t]);
+      };
+
+      // ring bookkeeping: item 2j = K(j), item 2j+1 = V(j)
+      auto item_stage = [&](int item) { return item % NS; };
+      auto item_phase = [&](int item) { return static_cast<uint32_t>((item / NS) & 1); };
+
+      if (n0 > 0) mbar_wait(&q_full[0], 0);
+      if (n1 > 0) mbar_wait(&q_full[1], 0);
+      mbar_wait(&kv_full[item_stage(0)], item_phase(0));
+      tc_fence_after();
+      for (int t = 0; t < 2; ++t)
+        if (nt[t] > 0) issue_qk(t, item_stage(0));
+      umma_commit(&kv_empty[item_stage(0)]);  // K(0) free once both S MMAs retire
+
+      for (int j = 0; j < n_max; ++j) {
+        const int v_item = 2 * j + 1, k_item = 2 * j + 2;
+        mbar_wait(&kv_full[item_stage(v_item)], item_phase(v_item));
+        const bool has_next = (j + 1 < n_max);
+        bool next_k_ready = false;
+        for (int t = 0; t < 2; ++t) {
+          if (j < nt[t]) {
+            mbar_wait(&p_full[t], static_cast<uint32_t>(j & 1));
+            tc_fence_after();
+            issue_pv(t, item_stage(v_item), j > 0);
+          }
+          if (j + 1 < nt[t]) {
+            if (!next_k_ready) {
+              mbar_wait(&kv_full[item_stage(k_item)], item_phase(k_item));
+              tc_fence_after();
+              next_k_ready = true;
+            }
+            issue_qk(t, item_stage(k_item));
+          }
+        }
+        umma_commit(&kv_empty[item_stage(v_item)]);
+        if (has_next) {
+          if (!next_k_ready) mbar_wait(&kv_full[item_stage(k_item)], item_phase(k_item));
+          umma_commit(&kv_empty[item_stage(k_item)]);
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ============================== softmax / correction / epilogue ==============================
+    setmaxnreg_inc<224>();
+    const int t = (warp_idx - 4) >> 2;           // query tile of this warpgroup
+    const int quad = warp_idx & 3;               // TMEM lane quadrant
+    const int row = quad * 32 + lane;            // row inside the tile
+    const int wg_tid = threadIdx.x - 128 - t * 128;
+    const int tile_row0 = q_row0 + t * BLOCK_M;
+    const int q_row = tile_row0 + row;
+    const int nt = t == 0 ? n0 : n1;
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + C::TMEM_S + static_cast<uint32_t>(t * 128);
+    const uint32_t tP = tS + C::TMEM_P_OFF;
+    const uint32_t tO = tmem_base + lane_addr + C::TMEM_O + static_cast<uint32_t>(t * D);
+    uint8_t* sO = smem + C::SMEM_Q_OFF + t * C::TILE_BYTES;  // Q_t's smem is reused for the output tile
+
+    float m_used = -INFINITY;  // reference max (log2 units) the stored P / O / l are relative to
+    float l_run = 0.f;
+    const int64_t q_pos_plus = static_cast<int64_t>(q_row) + p.causal_offset;  // last visible key under causal
+
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&s_full[t], static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      uint32_t s[128];
+      tmem_ld_x32(tS + 0, s + 0);
+      tmem_ld_x32(tS + 32, s + 32);
+      tmem_ld_x32(tS + 64, s + 64);
+      tmem_ld_x32(tS + 96, s + 96);
+      tmem_wait_ld();
+      // ---- masking: keys >= limit (relative to the tile) are invisible ----
+      const int kv0 = j * BLOCK_N;
+      int limit = kv_len - kv0;
+      if (p.causal) {
+        const int64_t cl = q_pos_plus - kv0 + 1;
+        if (cl < limit) limit = static_cast<int>(cl < 0 ? 0 : cl);
+      }
+      if (limit < BLOCK_N) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= limit) s[c] = 0xFF800000u;  // -inf
+      }
+      // ---- row max ----
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[c + 0]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      // ---- lazy rescale decision ----
+      float alpha = 1.0f;
+      bool rescale = false;
+      if (j == 0) {
+        m_used = m_tile;
+      } else if (m_tile > m_used + kRescaleThreshold) {
+        alpha = fast_exp2(m_used - m_tile);  // m_used = -inf -> 0
+        m_used = m_tile;
+        l_run *= alpha;
+        rescale = true;
+      }
+      if (__any_sync(0xffffffffu, rescale)) {
+        // O_t must contain P(j-1) V(j-1) before it is rescaled
+        mbar_wait(&pv_done[t], static_cast<uint32_t>((j - 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld_x32(tO + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x32(tO + c * 32, o);
+        }
+      }
+      // ---- P = exp2(s * scale - m_used), row sum, pack to 16 bit, store to TMEM ----
+      const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+      const float neg_m = -m_ref;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int c = half * 64 + i * 2;
+          const float e0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
+          sum0 += e0;
+          sum1 += e1;
+          pk[i] = Pack2<T>::pack(e0, e1);
+        }
+        tmem_st_x32(tP + half * 32, pk);
+      }
+      l_run += sum0 + sum1;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    // ---- epilogue: O / l -> 16 bit -> smem (128B swizzle) -> TMA store; LSE -> global ----
+    if (tile_row0 < p.Sq) {
+      float inv_l = 0.f;
+      float lse_val = -INFINITY;
+      if (nt > 0) {
+        mbar_wait(&pv_done[t], static_cast<uint32_t>((nt - 1) & 1));
+        tc_fence_after();
+        if (l_run > 0.f) {
+          inv_l = 1.0f / l_run;
+          lse_val = (m_used + log2f(l_run)) * kLn2;
+        }
+      } else {
+        mbar_wait(&q_full[t], 0);  // the Q tile load into this buffer must have landed before we overwrite it
+      }
+      if (p.lse != nullptr && q_row < p.Sq)
+        p.lse[(static_cast<int64_t>(batch) * p.Hq + head) * p.Sq + q_row] = lse_val;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        if (nt > 0) {
+          tmem_ld_x32(tO + c * 32, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0u;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 pk;
+          pk.x = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
+          pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
+          pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
+          pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
+          const int col = c * 32 + q4 * 8;       // first column of this 16-byte chunk
+          const int box = col >> 6;
+          const int c16 = (col & 63) >> 3;
+          *reinterpret_cast<uint4*>(sO + box * 16384 + row * 128 + ((c16 ^ (row & 7)) << 4)) = pk;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2 + t, 128);
+      if (wg_tid == 0) {
+#pragma unroll
+        for (int c = 0; c < C::BOXES; ++c) tma_store_4d(&tmap_o, sO + c * 16384, c * 64, head, tile_row0, batch);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D, typename T>
+int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, const Params& p,
+           cudaStream_t stream) {
+  auto kern = fa_fwd_kernel<D, T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(p.num_pairs, p.Hq, p.B);
+  kern<<<grid, NUM_THREADS, Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
+static int make_bshd_tmap(CUtensorMap* out, const void* base, int B, int S, int H, int D, const int64_t strides[3],
+                          const char* name) {
+  // tensor addressed as [b][s][h][d] with element strides (b, s, h); TMA dims innermost-first: (d, h, s, b)
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] <= 0 || strides[i] % 8 != 0)
+      return set_error(B200_ERR_INVALID_ARGUMENT, "%s stride %d = %lld must be a positive multiple of 8 elements", name,
+                       i, (long long)strides[i]);
+  uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(H), static_cast<uint64_t>(S),
+                      static_cast<uint64_t>(B)};
+  uint64_t str[3] = {static_cast<uint64_t>(strides[2]) * 2, static_cast<uint64_t>(strides[1]) * 2,
+                     static_cast<uint64_t>(strides[0]) * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return encode_tmap_sw128_16b(out, base, 4, dims, str, box);
+}
+
+}  // namespace fa
+}  // namespace b200
+
+extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Sq, int Sk,
+                           int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                           const int64_t v_strides[3], const int64_t o_strides[3], float softmax_scale, int causal,
+                           int64_t causal_offset, const int32_t* kv_lens, int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(q && k && v && o && q_strides && k_strides && v_strides && o_strides, "fa_fwd: NULL pointer argument");
+  B200_CHECK_ARG(B > 0 && Sq > 0 && Sk > 0 && Hq > 0 && Hkv > 0, "fa_fwd: bad sizes B=%d Sq=%d Sk=%d Hq=%d Hkv=%d", B, Sq,
+                 Sk, Hq, Hkv);
+  B200_CHECK_ARG(Hq % Hkv == 0, "fa_fwd: Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
+  B200_CHECK_ARG(D == 64 || D == 128, "fa_fwd: head_dim %d unsupported (64, 128)", D);
+  B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "fa_fwd: dtype must be bf16 or fp16");
+  B200_CHECK_ARG(softmax_scale > 0.f, "fa_fwd: softmax_scale must be positive");
+  B200_CHECK_ARG(B <= 65535 && Hq <= 65535, "fa_fwd: B and Hq must be <= 65535");
+  CUtensorMap tq, tk, tv, to;
+  int rc;
+  if ((rc = fa::make_bshd_tmap(&tq, q, B, Sq, Hq, D, q_strides, "q"))) return rc;
+  if ((rc = fa::make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
+  if ((rc = fa::make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
+  if ((rc = fa::make_bshd_tmap(&to, o, B, Sq, Hq, D, o_strides, "o"))) return rc;
+  fa::Params p;
+  p.lse = lse;
+  p.kv_lens = kv_lens;
+  p.B = B; p.Sq = Sq; p.Sk = Sk; p.Hq = Hq; p.Hkv = Hkv;
+  p.scale_log2 = softmax_scale * fa::kLog2e;
+  p.causal = causal ? 1 : 0;
+  p.causal_offset = causal_offset;
+  p.num_pairs = (Sq + 2 * fa::BLOCK_M - 1) / (2 * fa::BLOCK_M);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (D == 128) {
+    return dtype == B200_DTYPE_BF16 ? fa::launch<128, __nv_bfloat16>(tq, tk, tv, to, p, s)
+                                    : fa::launch<128, __half>(tq, tk, tv, to, p, s);
+  }
+  return dtype == B200_DTYPE_BF16 ? fa::launch<64, __nv_bfloat16>(tq, tk, tv, to, p, s)
+                                  : fa::launch<64, __half>(tq, tk, tv, to, p, s);
+}

@@ -1,0 +1,345 @@
+"""Torch-facing wrappers over the C-ABI (``include/b200_attn_mlp.h``).
+
+PyTorch is plumbing here: it owns device memory and streams; the arithmetic happens in the hand-written sm_100a
+kernels behind ``libb200_attn_mlp.so``. Every function raises (``B200Error`` / ``ValueError``) instead of falling
+back to eager PyTorch.
+
+Function ↔ reference map (paths under the reference tree):
+  flash_attn_fwd      ↔ kernels/triton/flash_attention_kernels.py:1150 ``triton_flash_attention``
+  decode_attention    ↔ kernels/triton/attention_kernels.py:1206 ``triton_paged_attention_forward``
+  kv_append           ↔ kernels/triton/attention_kernels.py:1314 ``triton_reshape_and_cache``
+  fused_mlp           ↔ kernels/triton/mlp_kernels.py:648 ``triton_fused_mlp``
+  lse_merge           ↔ kernels/triton/attention_kernels.py:1567-1585 (online-softmax merge algebra)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, ACT_RELU, ACT_SWIGLU, DTYPE_BF16, DTYPE_FP16, KV_CONTIGUOUS,
+                   KV_PAGED, check, strides3)
+
+_ACTIVATIONS = {
+    None: ACT_NONE, "none": ACT_NONE, "identity": ACT_NONE,
+    "gelu_tanh": ACT_GELU_TANH, "gelu_new": ACT_GELU_TANH, "gelu_pytorch_tanh": ACT_GELU_TANH,
+    "gelu": ACT_GELU_ERF, "gelu_erf": ACT_GELU_ERF,
+    "relu": ACT_RELU,
+    "swiglu": ACT_SWIGLU, "silu": ACT_SWIGLU,
+}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return DTYPE_BF16
+    if t.dtype == torch.float16:
+        return DTYPE_FP16
+    raise ValueError(f"b200 kernels compute on bf16/fp16 tensors, got {t.dtype}")
+
+
+def _require_cuda(*tensors: Optional[torch.Tensor]) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("b200 kernels need CUDA tensors: there is no CPU fallback for this path")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError("all tensors must be on the same CUDA device")
+    return dev
+
+
+def _stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _last_dim_contiguous(t: torch.Tensor) -> torch.Tensor:
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------
+# K1 prefill attention
+# --------------------------------------------------------------------------------------------------------
+def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False,
+                   softmax_scale: Optional[float] = None, causal_offset: int = 0,
+                   kv_lens: Optional[torch.Tensor] = None, return_lse: bool = False,
+                   out: Optional[torch.Tensor] = None):
+    """Attention forward. q ``[B,Sq,Hq,D]``, k/v ``[B,Sk,Hkv,D]`` (any batch/seq/head strides, D contiguous).
+
+    Returns ``o [B,Sq,Hq,D]`` (same dtype as q) and, if ``return_lse``, ``lse [B,Hq,Sq]`` fp32 (natural log).
+    ``causal_offset`` = global position of query row 0 minus global position of key row 0.
+    """
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError(f"expected 4-D [B,S,H,D] tensors, got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    dev = _require_cuda(q, k, v, kv_lens, out)
+    B, Sq, Hq, D = q.shape
+    Bk, Sk, Hkv, Dk = k.shape
+    if (Bk, Dk) != (B, D) or tuple(v.shape) != tuple(k.shape):
+        raise ValueError(f"q/k/v shapes do not match: {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("q, k, v must share a dtype")
+    dt = _dtype_code(q)
+    q, k, v = _last_dim_contiguous(q), _last_dim_contiguous(k), _last_dim_contiguous(v)
+    if out is None:
+        out = torch.empty((B, Sq, Hq, D), dtype=q.dtype, device=dev)
+    elif tuple(out.shape) != (B, Sq, Hq, D) or out.dtype != q.dtype or out.stride(-1) != 1:
+        raise ValueError("out must be [B,Sq,Hq,D], same dtype as q, D contiguous")
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
+    if kv_lens is not None:
+        if kv_lens.dtype != torch.int32 or kv_lens.numel() != B or not kv_lens.is_contiguous():
+            raise ValueError("kv_lens must be a contiguous int32 tensor of shape [B]")
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_fa_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(lse), B, Sq, Sk, Hq, Hkv, D,
+                             strides3(q.stride()[:3]), strides3(k.stride()[:3]), strides3(v.stride()[:3]),
+                             strides3(out.stride()[:3]), scale, int(bool(causal)), int(causal_offset), _ptr(kv_lens), dt,
+                             _stream_ptr(dev))
+    check("b200_fa_fwd", rc)
+    return (out, lse) if return_lse else out
+
+
+def lse_merge(o_acc: torch.Tensor, lse_acc: torch.Tensor, o_b: torch.Tensor, lse_b: torch.Tensor) -> None:
+    """In place: merge the partial result ``(o_b [B,Sq,Hq,D] 16-bit, lse_b [B,Hq,Sq])`` into the fp32 accumulator."""
+    dev = _require_cuda(o_acc, lse_acc, o_b, lse_b)
+    B, Sq, Hq, D = o_b.shape
+    if o_acc.dtype != torch.float32 or not o_acc.is_contiguous() or tuple(o_acc.shape) != (B, Sq, Hq, D):
+        raise ValueError("o_acc must be a contiguous fp32 [B,Sq,Hq,D] tensor")
+    for name, t in (("lse_acc", lse_acc), ("lse_b", lse_b)):
+        if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (B, Hq, Sq):
+            raise ValueError(f"{name} must be a contiguous fp32 [B,Hq,Sq] tensor")
+    o_b = _last_dim_contiguous(o_b)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_lse_merge(o_acc.data_ptr(), lse_acc.data_ptr(), o_b.data_ptr(), lse_b.data_ptr(), B, Sq, Hq, D,
+                                strides3(o_b.stride()[:3]), _dtype_code(o_b), _stream_ptr(dev))
+    check("b200_lse_merge", rc)
+
+
+def cast_out(o_acc: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = _require_cuda(o_acc, out)
+    B, Sq, Hq, D = o_acc.shape
+    if o_acc.dtype != torch.float32 or not o_acc.is_contiguous():
+        raise ValueError("o_acc must be a contiguous fp32 tensor")
+    if out is None:
+        out = torch.empty((B, Sq, Hq, D), dtype=dtype, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_cast_out(o_acc.data_ptr(), out.data_ptr(), B, Sq, Hq, D, strides3(out.stride()[:3]),
+                               _dtype_code(out), _stream_ptr(dev))
+    check("b200_cast_out", rc)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
+# K2 decode attention
+# --------------------------------------------------------------------------------------------------------
+_workspaces: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> Optional[torch.Tensor]:
+    """Per-(device, stream) grow-only scratch buffer (the C-ABI never allocates)."""
+    if nbytes <= 0:
+        return None
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _workspaces[key] = buf
+    return buf
+
+
+def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, context_lens: torch.Tensor,
+                     softmax_scale: Optional[float] = None, block_tables: Optional[torch.Tensor] = None,
+                     layer_idx: int = 0, max_context_len: Optional[int] = None, num_splits: int = 0,
+                     return_lse: bool = False, out: Optional[torch.Tensor] = None):
+    """Single-token attention against a KV cache.
+
+    q ``[B,Hq,D]``. Contiguous cache: k/v ``[B,S_max,Hkv,D]`` (``block_tables is None``). Paged cache: k/v
+    ``[num_blocks, L, block_size, Hkv, D]`` + ``block_tables`` int32 ``[B,max_blocks]`` + ``layer_idx``.
+    ``context_lens`` int32 ``[B]`` counts the valid keys (the appended token included).
+    """
+    dev = _require_cuda(q, k_cache, v_cache, context_lens, block_tables, out)
+    if q.dim() != 3:
+        raise ValueError(f"q must be [B,Hq,D], got {tuple(q.shape)}")
+    B, Hq, D = q.shape
+    dt = _dtype_code(q)
+    if k_cache.dtype != q.dtype or v_cache.dtype != q.dtype:
+        raise ValueError("cache dtype must match q")
+    if context_lens.dtype != torch.int32 or not context_lens.is_contiguous() or context_lens.numel() != B:
+        raise ValueError("context_lens must be a contiguous int32 [B] tensor")
+    q = q.contiguous()
+    paged = block_tables is not None
+    if paged:
+        if k_cache.dim() != 5 or not k_cache.is_contiguous() or not v_cache.is_contiguous():
+            raise ValueError("paged cache must be contiguous [num_blocks, L, block_size, Hkv, D]")
+        _, num_layers, block_size, Hkv, Dk = k_cache.shape
+        if block_tables.dtype != torch.int32 or block_tables.dim() != 2 or not block_tables.is_contiguous():
+            raise ValueError("block_tables must be a contiguous int32 [B, max_blocks] tensor")
+        max_blocks = block_tables.shape[1]
+        cap = max_blocks * block_size
+        kv_bs = kv_ts = 0
+        layout = KV_PAGED
+    else:
+        if k_cache.dim() != 4 or k_cache.stride(-1) != 1 or k_cache.stride(2) != k_cache.shape[3]:
+            raise ValueError("contiguous cache must be [B,S_max,Hkv,D] with (Hkv, D) dense")
+        if v_cache.stride() != k_cache.stride() or v_cache.shape != k_cache.shape:
+            raise ValueError("k_cache and v_cache must share shape and strides")
+        _, cap, Hkv, Dk = k_cache.shape
+        kv_bs, kv_ts = k_cache.stride(0), k_cache.stride(1)
+        num_layers, block_size, max_blocks = 1, 0, 0
+        layout = KV_CONTIGUOUS
+    if Dk != D:
+        raise ValueError("head_dim of q and cache differ")
+    if max_context_len is None:
+        max_context_len = cap
+    max_context_len = int(min(max_context_len, cap))
+    if out is None:
+        out = torch.empty((B, Hq, D), dtype=q.dtype, device=dev)
+    lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        splits = num_splits if num_splits > 0 else lib.b200_fa_decode_num_splits(B, Hkv, max_context_len)
+        ws_bytes = lib.b200_fa_decode_workspace_bytes(B, Hq, Hkv, D, max_context_len, splits)
+        ws = _workspace(dev, ws_bytes)
+        rc = lib.b200_fa_decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), _ptr(lse), B, Hq,
+                                Hkv, D, context_lens.data_ptr(), max_context_len, scale, layout, kv_bs, kv_ts,
+                                _ptr(block_tables), max_blocks, block_size, num_layers, int(layer_idx), splits,
+                                _ptr(ws), ws_bytes, dt, _stream_ptr(dev))
+    check("b200_fa_decode", rc)
+    return (out, lse) if return_lse else out
+
+
+def kv_append(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
+              context_lens: torch.Tensor, block_tables: Optional[torch.Tensor] = None, layer_idx: int = 0) -> None:
+    """Write the new token's K,V ``[B,Hkv,D]`` into the cache at position ``context_lens[b]-1``."""
+    dev = _require_cuda(key, value, k_cache, v_cache, context_lens, block_tables)
+    B, Hkv, D = key.shape
+    key, value = key.contiguous(), value.contiguous()
+    paged = block_tables is not None
+    if paged:
+        if not k_cache.is_contiguous() or not v_cache.is_contiguous() or k_cache.dim() != 5:
+            raise ValueError("paged cache must be contiguous [num_blocks, L, block_size, Hkv, D]")
+        _, num_layers, block_size, _, _ = k_cache.shape
+        max_blocks = block_tables.shape[1]
+        kv_bs = kv_ts = 0
+    else:
+        if k_cache.dim() != 4 or k_cache.stride(-1) != 1 or k_cache.stride(2) != D:
+            raise ValueError("contiguous cache must be [B,S_max,Hkv,D] with (Hkv, D) dense")
+        kv_bs, kv_ts = k_cache.stride(0), k_cache.stride(1)
+        num_layers, block_size, max_blocks = 1, 0, 0
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_kv_append(key.data_ptr(), value.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), B, Hkv, D,
+                                context_lens.data_ptr(), KV_PAGED if paged else KV_CONTIGUOUS, kv_bs, kv_ts,
+                                _ptr(block_tables), max_blocks, block_size, num_layers, int(layer_idx),
+                                _dtype_code(key), _stream_ptr(dev))
+    check("b200_kv_append", rc)
+
+
+# --------------------------------------------------------------------------------------------------------
+# K3 fused MLP
+# --------------------------------------------------------------------------------------------------------
+def activation_code(name) -> int:
+    try:
+        return _ACTIVATIONS[name]
+    except KeyError:
+        raise ValueError(f"unsupported activation {name!r}; supported: {sorted(k for k in _ACTIVATIONS if k)}") from None
+
+
+def _as_rows(x: torch.Tensor) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+    lead = tuple(x.shape[:-1])
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1 or (x2.shape[0] > 1 and x2.stride(0) % 8 != 0):
+        x2 = x2.contiguous()
+    return x2, lead
+
+
+def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, activation=None,
+               gate_weight: Optional[torch.Tensor] = None, gate_bias: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``act(x @ weight.T + bias)`` or, for SwiGLU, ``silu(x @ gate_weight.T + gate_bias) * (x @ weight.T + bias)``."""
+    dev = _require_cuda(x, weight, bias, gate_weight, gate_bias, out)
+    act = activation_code(activation)
+    dt = _dtype_code(x)
+    x2, lead = _as_rows(x)
+    T, K = x2.shape
+    N, Kw = weight.shape
+    if Kw != K:
+        raise ValueError(f"weight {tuple(weight.shape)} does not match input width {K}")
+    for t in (weight, bias, gate_weight, gate_bias):
+        if t is not None and t.dtype != x.dtype:
+            raise ValueError("weights and biases must have the dtype of x")
+    weight = weight.contiguous()
+    bias = None if bias is None else bias.contiguous()
+    if act == ACT_SWIGLU:
+        if gate_weight is None:
+            raise ValueError("SwiGLU needs gate_weight")
+        gate_weight = gate_weight.contiguous()
+        gate_bias = None if gate_bias is None else gate_bias.contiguous()
+    y = out.reshape(-1, N) if out is not None else torch.empty((T, N), dtype=x.dtype, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_linear_act(x2.data_ptr(), x2.stride(0) if T > 1 else K, weight.data_ptr(), _ptr(bias),
+                                 _ptr(gate_weight), _ptr(gate_bias), y.data_ptr(), y.stride(0) if T > 1 else N, T, K, N,
+                                 act, dt, _stream_ptr(dev))
+    check("b200_linear_act", rc)
+    return y.reshape(*lead, N)
+
+
+def fused_mlp(x: torch.Tensor, w_up: torch.Tensor, b_up: Optional[torch.Tensor], w_down: torch.Tensor,
+              b_down: Optional[torch.Tensor], activation: str = "gelu_tanh", w_gate: Optional[torch.Tensor] = None,
+              b_gate: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FusedMLP forward: ``act(x W_up^T + b_up) W_down^T + b_down`` (SwiGLU: ``silu(x W_gate^T + b_gate) * up``)."""
+    dev = _require_cuda(x, w_up, b_up, w_down, b_down, w_gate, b_gate, out)
+    act = activation_code(activation)
+    if act == ACT_NONE:
+        raise ValueError("fused_mlp needs an activation")
+    dt = _dtype_code(x)
+    x2, lead = _as_rows(x)
+    T, h = x2.shape
+    i, hw = w_up.shape
+    h_out, iw = w_down.shape
+    if hw != h or iw != i:
+        raise ValueError(f"weight shapes {tuple(w_up.shape)} / {tuple(w_down.shape)} do not match input width {h}")
+    for t in (w_up, b_up, w_down, b_down, w_gate, b_gate):
+        if t is not None and t.dtype != x.dtype:
+            raise ValueError("weights and biases must have the dtype of x")
+    w_up, w_down = w_up.contiguous(), w_down.contiguous()
+    if act == ACT_SWIGLU:
+        if w_gate is None or tuple(w_gate.shape) != (i, h):
+            raise ValueError("SwiGLU needs w_gate of shape [intermediate, hidden]")
+        w_gate = w_gate.contiguous()
+    else:
+        w_gate = b_gate = None
+    b_up = None if b_up is None else b_up.contiguous()
+    b_down = None if b_down is None else b_down.contiguous()
+    b_gate = None if b_gate is None else b_gate.contiguous()
+    y = out.reshape(-1, h_out) if out is not None else torch.empty((T, h_out), dtype=x.dtype, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.b200_fused_mlp_workspace_bytes(T, h, i)
+        ws = _workspace(dev, ws_bytes)
+        rc = lib.b200_fused_mlp(x2.data_ptr(), x2.stride(0) if T > 1 else h, w_up.data_ptr(), _ptr(b_up), _ptr(w_gate),
+                                _ptr(b_gate), w_down.data_ptr(), _ptr(b_down), y.data_ptr(),
+                                y.stride(0) if T > 1 else h_out, T, h, i, h_out, act, _ptr(ws), ws_bytes, dt,
+                                _stream_ptr(dev))
+    check("b200_fused_mlp", rc)
+    return y.reshape(*lead, h_out)
+
+
+def arch_ok() -> bool:
+    return _lib.load().b200_arch_ok() == 1
+
+
+def version() -> str:
+    return _lib.load().b200_version().decode()
