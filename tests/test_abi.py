@@ -1,0 +1,76 @@
+"""CPU-only checks of the drop-in boundary: the library builds, loads, exports every symbol the header declares, and
+fails loudly (no fallback) when there is no GPU or an argument is wrong."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from ml_inference_optimizer_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported(built_lib):
+    header = open(os.path.join(ROOT, "include", "b200_attn_mlp.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(built_lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_header_cites_reference_interfaces():
+    header = open(os.path.join(ROOT, "include", "b200_attn_mlp.h")).read()
+    for cite in ("flash_attention_kernels.py:1150", "attention_kernels.py:1206", "attention_kernels.py:1314",
+                 "mlp_kernels.py:648", "tensor_parallel.py:173"):
+        assert cite in header
+
+
+def test_version_and_pure_host_queries(built_lib):
+    assert b"sm_100a" in built_lib.b200_version()
+    assert built_lib.b200_fused_mlp_workspace_bytes(32768, 4096, 11008) == 32768 * 11008 * 2
+    assert built_lib.b200_fa_decode_workspace_bytes(4, 32, 8, 128, 8192, 1) == 0
+    assert built_lib.b200_fa_decode_workspace_bytes(4, 32, 8, 128, 8192, 4) == 4 * 32 * 4 * 129 * 4
+
+
+def test_invalid_arguments_return_error_codes(built_lib):
+    s3 = _lib.strides3((1024, 128, 128))
+    rc = built_lib.b200_fa_fwd(None, None, None, None, None, 1, 128, 128, 1, 1, 128, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
+    assert rc == -1 and "NULL" in _lib.last_error()
+    dummy = ctypes.c_void_p(256)
+    rc = built_lib.b200_fa_fwd(dummy, dummy, dummy, dummy, None, 1, 128, 128, 3, 2, 128, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
+    assert rc == -1 and "multiple of Hkv" in _lib.last_error()
+    rc = built_lib.b200_fa_fwd(dummy, dummy, dummy, dummy, None, 1, 128, 128, 2, 2, 96, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
+    assert rc == -1 and "head_dim" in _lib.last_error()
+    rc = built_lib.b200_linear_act(dummy, 60, dummy, None, None, None, dummy, 64, 8, 60, 64, 0, 0, None)
+    assert rc == -1 and "multiples of 8" in _lib.last_error()
+    rc = built_lib.b200_fused_mlp(dummy, 64, dummy, None, None, None, dummy, None, dummy, 64, 8, 64, 128, 64, 1, None, 0, 0, None)
+    assert rc == -5 and "workspace" in _lib.last_error()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from ml_inference_optimizer_b200 import ops
+
+    assert _lib.load().b200_arch_ok() < 0  # B200_ERR_NO_DEVICE
+    q = torch.randn(1, 128, 1, 128, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.flash_attn_fwd(q, q, q)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.fused_mlp(torch.randn(4, 64, dtype=torch.bfloat16), torch.randn(128, 64, dtype=torch.bfloat16), None,
+                      torch.randn(64, 128, dtype=torch.bfloat16), None, "relu")
+
+
+def test_product_package_never_imports_the_oracle():
+    import re as _re
+
+    for top in ("ml_inference_optimizer_b200", "kernels", "parallelism", "baseline", "ml_inference_optimizer"):
+        pkg = os.path.join(ROOT, top)
+        for dirpath, _, files in os.walk(pkg):
+            for f in files:
+                if f.endswith(".py"):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not _re.search(r"^\s*(from|import)\s+oracle\b", text, _re.M), f"{top}/{f} imports the oracle"
