@@ -84,7 +84,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* pv_done = p_full + 2;                                          // [2]  MMA -> softmax (O_t updated)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp_idx = threadIdx.x >> 5;
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
 
   // heavy (late) query tiles first under a causal mask
@@ -127,10 +127,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // register budget: 384 threads x 168 at launch; the producer warpgroup gives 112 per thread to the softmax
-  // warpgroups (128 x 56 + 256 x 224 = 64512)
+  // register budget: 384 threads x 168 at launch; the producer warpgroup gives 96 per thread to the softmax
+  // warpgroups (128 x 72 + 256 x 216 = 64512)
   if (warp_idx < 4) {
-    setmaxnreg_dec<56>();
+    setmaxnreg_dec<72>();
   }
   if (warp_idx == 0) {
     // ============================== TMA producer ==============================
@@ -162,79 +162,100 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
   } else if (warp_idx == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0 && n_max > 0) {
+    // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one elected
+    // lane issues the tcgen05 instructions.
+    if (n_max > 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(BLOCK_M, BLOCK_N, Pack2<T>::kIsBf16, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(BLOCK_M, D, Pack2<T>::kIsBf16, false, true);
       const uint32_t sq_addr = smem_u32(smem + C::SMEM_Q_OFF);
       const uint32_t skv_addr = smem_u32(smem + C::SMEM_KV_OFF);
-      const int nt[2] = {n0, n1};
+      // descriptor templates; the start-address field (bits 0-13, 16-byte units) is advanced by plain adds
+      const uint64_t qdesc0 = make_smem_desc_sw128(sq_addr, 16, 1024);
+      const uint64_t kdesc0 = make_smem_desc_sw128(skv_addr, 16, 1024);
+      const uint64_t vdesc0 = make_smem_desc_sw128(skv_addr, 16384, 1024);
+      constexpr uint32_t TILE16 = C::TILE_BYTES >> 4;
 
       auto issue_qk = [&](int t, int k_stage) {
-        const uint32_t qa = sq_addr + t * C::TILE_BYTES;
-        const uint32_t ka = skv_addr + k_stage * C::TILE_BYTES;
+        const uint64_t qd = qdesc0 + static_cast<uint64_t>(t * TILE16);
+        const uint64_t kd = kdesc0 + static_cast<uint64_t>(k_stage * TILE16);
         const uint32_t d_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-          umma_ss(d_tmem, make_smem_desc_sw128(qa + off, 16, 1024), make_smem_desc_sw128(ka + off, 16, 1024),
-                  idesc_qk, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;  // 16-byte units: next 64-col box / next 32 bytes
+            umma_ss(d_tmem, qd + off, kd + off, idesc_qk, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[t]);
         }
-        umma_commit(&s_full[t]);
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int v_stage, bool accumulate) {
-        const uint32_t va = skv_addr + v_stage * C::TILE_BYTES;
+        const uint64_t vd = vdesc0 + static_cast<uint64_t>(v_stage * TILE16);
         const uint32_t d_tmem = tmem_base + C::TMEM_O + static_cast<uint32_t>(t * D);
         const uint32_t p_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128) + C::TMEM_P_OFF;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < BLOCK_N / 16; ++ks) {
-          umma_ts(d_tmem, p_tmem + ks * 8, make_smem_desc_sw128(va + ks * 2048, 16384, 1024), idesc_pv,
-                  (accumulate || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < BLOCK_N / 16; ++ks) {
+            umma_ts(d_tmem, p_tmem + ks * 8, vd + static_cast<uint64_t>(ks * 128), idesc_pv,
+                    (accumulate || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[t]);
         }
-        umma_commit(&pv_done[t]);
+        __syncwarp();
       };
-
-      // ring bookkeeping: item 2j = K(j), item 2j+1 = V(j)
-      auto item_stage = [&](int item) { return item % NS; };
-      auto item_phase = [&](int item) { return static_cast<uint32_t>((item / NS) & 1); };
+      auto release = [&](int stage) {
+        if (elect_one()) umma_commit(&kv_empty[stage]);
+        __syncwarp();
+      };
 
       if (n0 > 0) mbar_wait(&q_full[0], 0);
       if (n1 > 0) mbar_wait(&q_full[1], 0);
-      mbar_wait(&kv_full[item_stage(0)], item_phase(0));
+      // ring bookkeeping: item 2j = K(j), item 2j+1 = V(j); (stage, phase) advance by one per item
+      int k_stage = 0;          // stage of K(j+1) while in iteration j (K(0) before the loop)
+      uint32_t k_phase = 0;
+      mbar_wait(&kv_full[k_stage], k_phase);
       tc_fence_after();
-      for (int t = 0; t < 2; ++t)
-        if (nt[t] > 0) issue_qk(t, item_stage(0));
-      umma_commit(&kv_empty[item_stage(0)]);  // K(0) free once both S MMAs retire
+      if (n0 > 0) issue_qk(0, k_stage);
+      if (n1 > 0) issue_qk(1, k_stage);
+      release(k_stage);  // K(0) is free once both S MMAs retire
 
       for (int j = 0; j < n_max; ++j) {
-        const int v_item = 2 * j + 1, k_item = 2 * j + 2;
-        mbar_wait(&kv_full[item_stage(v_item)], item_phase(v_item));
+        int v_stage = k_stage + 1;
+        uint32_t v_phase = k_phase;
+        if (v_stage == NS) { v_stage = 0; v_phase ^= 1; }
+        k_stage = v_stage + 1;
+        k_phase = v_phase;
+        if (k_stage == NS) { k_stage = 0; k_phase ^= 1; }
+        mbar_wait(&kv_full[v_stage], v_phase);
         const bool has_next = (j + 1 < n_max);
         bool next_k_ready = false;
+#pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (j < nt[t]) {
+          const int nt_t = t == 0 ? n0 : n1;
+          if (j < nt_t) {
             mbar_wait(&p_full[t], static_cast<uint32_t>(j & 1));
             tc_fence_after();
-            issue_pv(t, item_stage(v_item), j > 0);
+            issue_pv(t, v_stage, j > 0);
           }
-          if (j + 1 < nt[t]) {
+          if (j + 1 < nt_t) {
             if (!next_k_ready) {
-              mbar_wait(&kv_full[item_stage(k_item)], item_phase(k_item));
+              mbar_wait(&kv_full[k_stage], k_phase);
               tc_fence_after();
               next_k_ready = true;
             }
-            issue_qk(t, item_stage(k_item));
+            issue_qk(t, k_stage);
           }
         }
-        umma_commit(&kv_empty[item_stage(v_item)]);
+        release(v_stage);
         if (has_next) {
-          if (!next_k_ready) mbar_wait(&kv_full[item_stage(k_item)], item_phase(k_item));
-          umma_commit(&kv_empty[item_stage(k_item)]);
+          if (!next_k_ready) mbar_wait(&kv_full[k_stage], k_phase);
+          release(k_stage);
         }
       }
     }
   } else if (warp_idx >= 4) {
     // ============================== softmax / correction / epilogue ==============================
-    setmaxnreg_inc<224>();
+    setmaxnreg_inc<216>();
     const int t = (warp_idx - 4) >> 2;           // query tile of this warpgroup
     const int quad = warp_idx & 3;               // TMEM lane quadrant
     const int row = quad * 32 + lane;            // row inside the tile

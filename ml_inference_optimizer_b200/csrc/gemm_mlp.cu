@@ -110,7 +110,7 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp_idx = threadIdx.x >> 5;
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
 
   if (warp_idx == 0 && lane == 0) {
@@ -168,33 +168,37 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, Pack2<T>::kIsBf16, false, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, Pack2<T>::kIsBf16, false, false);
+    const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem + SMEM_A_OFF), 16, 1024);
+    const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem + SMEM_B_OFF), 16, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + SMEM_A_OFF + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem + SMEM_B_OFF + stage * B_STAGE_BYTES);
+        const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * (A_STAGE_BYTES >> 4));
+        const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (B_STAGE_BYTES >> 4));
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t a_desc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t b_desc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss(d_tmem, a_desc, b_desc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, ad + static_cast<uint64_t>(k * 2), bd + static_cast<uint64_t>(k * 2), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================

@@ -316,6 +316,6 @@ def test_mlp_full_size_linearity(ops):
     assert torch.equal(y[rows], y_rows)
     c = lambda t: t.cpu()
     ref = orc.mlp_ref(c(x[rows]), c(wu), c(bu), c(wd), c(bd), "swiglu", c(wg), c(bg))
-    check_out(y_rows, ref, max_abs=3e-2, mean_rel=1e-2)
+    check_out(y_rows, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=1e-2)
     y0 = ops.fused_mlp(x[:512].contiguous(), wu, bu, torch.zeros_like(wd), bd, "swiglu", wg, bg)
     assert torch.equal(y0, bd.view(1, -1).expand(512, -1))
