@@ -1,0 +1,244 @@
+"""Mirror of the ring / sequence-parallel slice of the reference's ``parallelism/sequence_parallel.py``.
+
+``SequenceParallelAttention`` keeps the constructor, attribute names (``query``, ``key``, ``value``, ``output``) and
+``forward(hidden_states[B,S/sp,h], attention_mask)`` of the reference (:345-640); ``attention_handling="ring"`` is the
+exact, overlapped ring of ``parallelism/ring.py`` (the reference's is an approximation, F7), ``"local"`` attends to
+the local shard only (:480-517) and ``"full"`` all-gathers K,V (:587-640).
+Additions (keyword-only, defaults preserve the reference behaviour): ``causal`` and ``partition`` ("contiguous" |
+"zigzag").
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import communication as comm
+from .communication import get_rank
+from .ring import CudaRingBackend, ring_attention_forward
+
+__all__ = ["SequenceParallelConfig", "SequenceParallelAttention", "SequenceParallelMLP", "SequenceShardedModule",
+           "SequenceParallelConverter", "partition_sequence", "gather_sequence", "create_sequence_parallel_attention_mask"]
+
+
+@dataclass
+class SequenceParallelConfig:
+    """reference :22-85."""
+    world_size: int = 1
+    sp_size: int = 1
+    overlap_communication: bool = True
+    attention_handling: str = "ring"
+    chunk_size: Optional[int] = None
+    buffer_reuse: bool = True
+    communication_dtype: torch.dtype = torch.float16
+
+    def __post_init__(self):
+        if self.world_size % self.sp_size != 0:
+            raise ValueError(f"Sequence parallel size ({self.sp_size}) must divide world size ({self.world_size})")
+        if self.attention_handling not in ["local", "ring", "full"]:
+            raise ValueError(f"Attention handling strategy '{self.attention_handling}' not supported. "
+                             f"Use 'local', 'ring', or 'full'.")
+        if self.chunk_size is not None and self.chunk_size <= 0:
+            raise ValueError(f"Chunk size must be positive, got {self.chunk_size}")
+
+    def get_sp_group(self) -> Optional[dist.ProcessGroup]:
+        if not dist.is_initialized() or self.sp_size == 1:
+            return None
+        return comm.setup_sequence_parallel_group(self.world_size, self.sp_size)  # cached, not re-created per call
+
+    def get_dp_size(self) -> int:
+        return self.world_size // self.sp_size
+
+    def get_rank_info(self) -> Tuple[int, int]:
+        rank = get_rank()
+        return rank % self.sp_size, rank // self.sp_size
+
+
+def partition_sequence(tensor: torch.Tensor, config: SequenceParallelConfig, partition: str = "contiguous") -> torch.Tensor:
+    sp_rank, _ = config.get_rank_info()
+    return comm.scatter_along_sequence_dim(tensor, config.sp_size, partition=partition, rank=sp_rank)
+
+
+def gather_sequence(tensor: torch.Tensor, config: SequenceParallelConfig, partition: str = "contiguous") -> torch.Tensor:
+    return comm.gather_along_sequence_dim(tensor, config.sp_size, partition=partition, group=config.get_sp_group())
+
+
+def create_sequence_parallel_attention_mask(attention_mask: Optional[torch.Tensor], config: SequenceParallelConfig):
+    """Key-padding masks are lowered to lengths inside the attention module; additive 4-D masks are not supported on the
+    CUDA path, so this returns the mask untouched for the caller to pass on (reference :882-940 slices it per rank)."""
+    return attention_mask
+
+
+class SequenceParallelAttention(nn.Module):
+    """reference :345-640."""
+
+    def __init__(self, hidden_size: int, num_attention_heads: int, config: SequenceParallelConfig,
+                 attention_dropout: float = 0.1, head_dim: Optional[int] = None, bias: bool = True, *,
+                 causal: bool = False, partition: str = "contiguous", backend=None):
+        super().__init__()
+        self.config = config
+        self.hidden_size = hidden_size
+        self.num_attention_heads = num_attention_heads
+        self.head_dim = head_dim if head_dim is not None else hidden_size // num_attention_heads
+        self.all_head_size = self.num_attention_heads * self.head_dim
+        self.query = nn.Linear(hidden_size, self.all_head_size, bias=bias)
+        self.key = nn.Linear(hidden_size, self.all_head_size, bias=bias)
+        self.value = nn.Linear(hidden_size, self.all_head_size, bias=bias)
+        self.output = nn.Linear(self.all_head_size, hidden_size, bias=bias)
+        self.dropout = nn.Dropout(attention_dropout)
+        self.causal = causal
+        self.partition = partition
+        self.backend = backend or CudaRingBackend()
+        self.sp_group = config.get_sp_group()
+        self.sp_rank, self.dp_rank = config.get_rank_info()
+        self.attention_impl = self._select_attention_impl()
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for lin in (self.query, self.key, self.value, self.output):
+            nn.init.xavier_uniform_(lin.weight)
+            if lin.bias is not None:
+                nn.init.zeros_(lin.bias)
+
+    def _select_attention_impl(self) -> Callable:
+        return {"local": self._local_attention, "ring": self._ring_attention, "full": self._full_attention}[
+            self.config.attention_handling]
+
+    def _transpose_for_scores(self, x: torch.Tensor) -> torch.Tensor:
+        """[B,S,all_head] -> [B,H,S,D] (a view; the kernels take the strides)."""
+        return x.view(*x.size()[:-1], self.num_attention_heads, self.head_dim).permute(0, 2, 1, 3)
+
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if attention_mask is not None:
+            raise NotImplementedError("additive attention masks are not supported on the ring path; use causal=True")
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("attention dropout is not implemented (inference path)")
+        q = self._transpose_for_scores(self.query(hidden_states))
+        k = self._transpose_for_scores(self.key(hidden_states))
+        v = self._transpose_for_scores(self.value(hidden_states))
+        ctx = self.attention_impl(q=q, k=k, v=v, attention_mask=None)  # [B,H,S,D]
+        ctx = ctx.permute(0, 2, 1, 3)
+        ctx = ctx.reshape(*ctx.size()[:-2], self.all_head_size)
+        return self.output(ctx)
+
+    # all three take/return [B,H,S/sp,D] like the reference
+    def _local_attention(self, q, k, v, attention_mask=None):
+        o, _ = self.backend.attn(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), self.causal, None)
+        return o.transpose(1, 2)
+
+    def _ring_attention(self, q, k, v, attention_mask=None):
+        o = ring_attention_forward(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=self.causal,
+                                   group=self.sp_group, partition=self.partition, backend=self.backend,
+                                   overlap=self.config.overlap_communication)
+        return o.transpose(1, 2)
+
+    def _full_attention(self, q, k, v, attention_mask=None):
+        kf = comm.gather_along_sequence_dim(k.transpose(1, 2).contiguous(), self.config.sp_size, self.partition, self.sp_group)
+        vf = comm.gather_along_sequence_dim(v.transpose(1, 2).contiguous(), self.config.sp_size, self.partition, self.sp_group)
+        if self.causal:
+            if self.partition != "contiguous":
+                raise NotImplementedError("full (all-gather) causal attention needs the contiguous partition")
+            s_local = q.shape[2]
+            o, _ = self._attn_offset(q.transpose(1, 2), kf, vf, self.sp_rank * s_local)
+        else:
+            o, _ = self.backend.attn(q.transpose(1, 2), kf, vf, False, None)
+        return o.transpose(1, 2)
+
+    def _attn_offset(self, q, k, v, offset):
+        from .. import ops
+        return ops.flash_attn_fwd(q, k, v, causal=True, causal_offset=offset, return_lse=True)
+
+
+class SequenceParallelMLP(nn.Module):
+    """reference :643-720 — token-wise, so every rank runs the fused MLP on its own sequence shard; no communication."""
+
+    def __init__(self, hidden_size: int, intermediate_size: int, config: SequenceParallelConfig,
+                 activation: Callable = F.gelu, dropout_prob: float = 0.1, bias: bool = True):
+        super().__init__()
+        self.config = config
+        self.dense_h_to_4h = nn.Linear(hidden_size, intermediate_size, bias=bias)
+        self.dense_4h_to_h = nn.Linear(intermediate_size, hidden_size, bias=bias)
+        self.activation = activation
+        self.dropout = nn.Dropout(dropout_prob)
+        self.sp_group = config.get_sp_group()
+        self.sp_rank, self.dp_rank = config.get_rank_info()
+        nn.init.xavier_uniform_(self.dense_h_to_4h.weight)
+        nn.init.xavier_uniform_(self.dense_4h_to_h.weight)
+        if bias:
+            nn.init.zeros_(self.dense_h_to_4h.bias)
+            nn.init.zeros_(self.dense_4h_to_h.bias)
+
+    def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        from .tensor_parallel import activation_name
+        from .. import ops
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout is not implemented (inference path)")
+        return ops.fused_mlp(hidden_states, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight,
+                             self.dense_4h_to_h.bias, activation_name(self.activation))
+
+
+class SequenceShardedModule(nn.Module):
+    """reference :88-343 reduced to its data path: narrow ``[B,S,h]`` to this rank's shard, run the wrapped module,
+    all-gather the result along the sequence on the SP group."""
+
+    def __init__(self, module: nn.Module, config: SequenceParallelConfig, partition: str = "contiguous"):
+        super().__init__()
+        self.module = module
+        self.config = config
+        self.partition = partition
+
+    def forward(self, hidden_states: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        local = partition_sequence(hidden_states, self.config, self.partition)
+        out = self.module(local.contiguous(), *args, **kwargs)
+        if isinstance(out, tuple):
+            out = out[0]
+        return gather_sequence(out, self.config, self.partition)
+
+
+class SequenceParallelConverter:
+    """reference :723-879 — swaps attention modules that expose ``query/key/value/output`` or ``q_proj/k_proj/v_proj/
+    o_proj`` Linears for ``SequenceParallelAttention`` and COPIES their weights (the reference creates fresh random
+    modules, Appendix B)."""
+
+    def __init__(self, config: SequenceParallelConfig, causal: bool = False, partition: str = "contiguous"):
+        self.config = config
+        self.causal = causal
+        self.partition = partition
+
+    def convert_model(self, model: nn.Module) -> nn.Module:
+        for name, sub in list(model.named_children()):
+            new = self._convert(sub)
+            if new is not None:
+                setattr(model, name, new)
+            else:
+                self.convert_model(sub)
+        return model
+
+    def _convert(self, m: nn.Module) -> Optional[nn.Module]:
+        if isinstance(m, SequenceParallelAttention):
+            return None
+        names = None
+        if all(hasattr(m, a) for a in ("query", "key", "value", "output")):
+            names = ("query", "key", "value", "output")
+        elif all(hasattr(m, a) for a in ("q_proj", "k_proj", "v_proj", "o_proj")):
+            names = ("q_proj", "k_proj", "v_proj", "o_proj")
+        if names is None or not all(isinstance(getattr(m, a), nn.Linear) for a in names):
+            return None
+        q = getattr(m, names[0])
+        heads = getattr(m, "num_attention_heads", None) or getattr(m, "num_heads", None)
+        if heads is None or getattr(m, names[1]).out_features != q.out_features:
+            return None
+        new = SequenceParallelAttention(q.in_features, heads, self.config, attention_dropout=0.0,
+                                        head_dim=q.out_features // heads, bias=q.bias is not None, causal=self.causal,
+                                        partition=self.partition)
+        with torch.no_grad():
+            for dst, src in zip((new.query, new.key, new.value, new.output), (getattr(m, a) for a in names)):
+                dst.weight.copy_(src.weight)
+                if src.bias is not None:
+                    dst.bias.copy_(src.bias)
+        return new.to(device=q.weight.device, dtype=q.weight.dtype)

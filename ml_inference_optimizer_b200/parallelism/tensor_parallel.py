@@ -1,0 +1,279 @@
+"""Mirror of the hot-path slice of the reference's ``parallelism/tensor_parallel.py`` (Megatron-style column / row
+split): ``ColumnParallelLinear`` (:88-204), ``RowParallelLinear`` (:207-327), ``TensorParallelMLP`` (:330-400) and
+``TensorParallelAttention`` (:403-599), on the sm_100a kernels.
+
+``TensorParallelMLP`` runs K3 on the rank's shard — up/gate GEMM with the activation fused in the epilogue, then the
+down GEMM over the rank's columns — followed by ONE all-reduce (NCCL; NVLS in-switch reduction on the NVSwitch box)
+and the bias added once after the reduction (reference :302-308). ``TensorParallelAttention`` runs K1 on Hq/tp query
+heads and Hkv/tp KV heads; its row-parallel output projection carries the only all-reduce.
+Reference defects not reproduced (Appendix B): K/V projections aliased to Q (:481-483), converters that drop the
+weights (:684-690), the ``num_partitions`` keyword mismatch (:293).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import communication as comm
+from . import parallel_utils as pu
+
+__all__ = ["TensorParallelConfig", "ColumnParallelLinear", "RowParallelLinear", "TensorParallelMLP",
+           "TensorParallelAttention", "ModelParallelConverter", "activation_name"]
+
+
+def activation_name(fn) -> str:
+    """Map the reference's activation callables (``F.gelu`` default, :336) to the fused-epilogue selector."""
+    if isinstance(fn, str):
+        return fn
+    name = getattr(fn, "__name__", type(fn).__name__).lower()
+    if getattr(fn, "keywords", None) and fn.keywords.get("approximate") == "tanh":
+        return "gelu_tanh"
+    if isinstance(fn, nn.GELU):
+        return "gelu_tanh" if fn.approximate == "tanh" else "gelu_erf"
+    if "gelu_new" in name or "newgelu" in name or "gelu_tanh" in name:
+        return "gelu_tanh"
+    if "gelu" in name:
+        return "gelu_erf"
+    if "relu" in name:
+        return "relu"
+    if "silu" in name or "swish" in name or "swiglu" in name:
+        return "swiglu"
+    raise ValueError(f"activation {fn!r} has no fused epilogue (supported: gelu, gelu_tanh, relu, silu/swiglu)")
+
+
+class TensorParallelConfig:
+    """reference :16-85. ``get_tp_group`` returns the group made by ``parallel_utils.initialize_tensor_parallel``
+    (the reference returns None)."""
+
+    def __init__(self, world_size: int = 1, tp_size: int = 1, dp_size: Optional[int] = None, parallel_dim: int = -1,
+                 gather_output: bool = True, recompute_activation: bool = False,
+                 communication_dtype: torch.dtype = torch.float16, sequence_parallel: bool = False,
+                 gradient_accumulation_steps: int = 1, use_cpu_initialization: bool = False):
+        self.world_size = world_size
+        self.tp_size = tp_size
+        if dp_size is None:
+            assert world_size % tp_size == 0, "World size must be divisible by tensor parallel size"
+            self.dp_size = world_size // tp_size
+        else:
+            self.dp_size = dp_size
+            assert world_size == tp_size * dp_size, "World size must equal tp_size * dp_size"
+        self.parallel_dim = parallel_dim
+        self.gather_output = gather_output
+        self.recompute_activation = recompute_activation
+        self.communication_dtype = communication_dtype
+        self.sequence_parallel = sequence_parallel
+        self.gradient_accumulation_steps = gradient_accumulation_steps
+        self.use_cpu_initialization = use_cpu_initialization
+
+    def get_tp_group(self):
+        if not dist.is_initialized() or self.tp_size == 1:
+            return None
+        g = pu.get_tensor_model_parallel_group()
+        return g if g is not None else pu.initialize_tensor_parallel(self.tp_size)
+
+    def get_dp_group(self):
+        return None
+
+    def tp_rank(self) -> int:
+        g = self.get_tp_group()
+        return dist.get_rank(g) if g is not None else 0
+
+
+def _linear(x, w, b, local_linear=None):
+    if local_linear is not None:
+        return local_linear(x, w, b)
+    from .. import ops
+    return ops.linear_act(x, w, b)
+
+
+class ColumnParallelLinear(nn.Module):
+    """reference :88-204 — weight ``[out/tp, in]``; optional all-gather of the output."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, config: Optional[TensorParallelConfig] = None,
+                 gather_output: Optional[bool] = None, stride: int = 1, skip_bias_add: bool = False):
+        super().__init__()
+        self.config = config or TensorParallelConfig()
+        self.in_features, self.out_features = in_features, out_features
+        self.gather_output = self.config.gather_output if gather_output is None else gather_output
+        self.skip_bias_add = skip_bias_add
+        self.tp_size = self.config.tp_size
+        self.output_size_per_partition = pu.divide(out_features, self.tp_size)
+        self.weight = nn.Parameter(torch.empty(self.output_size_per_partition, in_features))
+        self.bias = nn.Parameter(torch.zeros(self.output_size_per_partition)) if bias else None
+        nn.init.normal_(self.weight, std=0.02)
+        self._local_linear = None  # test hook (CPU/gloo host-logic tests)
+
+    def load_full(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        r = self.config.tp_rank()
+        s = self.output_size_per_partition
+        with torch.no_grad():
+            self.weight.copy_(weight[r * s:(r + 1) * s])
+            if self.bias is not None and bias is not None:
+                self.bias.copy_(bias[r * s:(r + 1) * s])
+
+    def forward(self, x: torch.Tensor):
+        b = None if self.skip_bias_add else self.bias
+        y = _linear(x, self.weight, b, self._local_linear)
+        if self.gather_output and self.tp_size > 1:
+            y = pu.gather_tensor_along_dim(y, -1, self.config.get_tp_group())
+        return (y, self.bias) if self.skip_bias_add else y
+
+
+class RowParallelLinear(nn.Module):
+    """reference :207-327 — weight ``[out, in/tp]``; all-reduce(sum) of the partial outputs, bias added after (:302-308)."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, config: Optional[TensorParallelConfig] = None,
+                 input_is_parallel: bool = False, stride: int = 1, skip_bias_add: bool = False):
+        super().__init__()
+        self.config = config or TensorParallelConfig()
+        self.in_features, self.out_features = in_features, out_features
+        self.input_is_parallel = input_is_parallel
+        self.skip_bias_add = skip_bias_add
+        self.tp_size = self.config.tp_size
+        self.input_size_per_partition = pu.divide(in_features, self.tp_size)
+        self.weight = nn.Parameter(torch.empty(out_features, self.input_size_per_partition))
+        self.bias = nn.Parameter(torch.zeros(out_features)) if bias else None
+        nn.init.normal_(self.weight, std=0.02)
+        self._local_linear = None
+
+    def load_full(self, weight: torch.Tensor, bias: Optional[torch.Tensor] = None):
+        r = self.config.tp_rank()
+        s = self.input_size_per_partition
+        with torch.no_grad():
+            self.weight.copy_(weight[:, r * s:(r + 1) * s])
+            if self.bias is not None and bias is not None:
+                self.bias.copy_(bias)
+
+    def forward(self, x: torch.Tensor):
+        if not self.input_is_parallel and self.tp_size > 1:
+            x = pu.split_tensor_along_dim(x, -1, num_partitions=self.tp_size)[self.config.tp_rank()].contiguous()
+        y = _linear(x, self.weight, None, self._local_linear)
+        if self.tp_size > 1:
+            comm.all_reduce(y, group=self.config.get_tp_group())
+        if self.skip_bias_add:
+            return y, self.bias
+        return y if self.bias is None else y + self.bias
+
+
+class TensorParallelMLP(nn.Module):
+    """reference :330-400 — ``dense_h_to_4h`` column-parallel (no gather) -> activation -> ``dense_4h_to_h`` row-parallel.
+    ``gated=True`` adds the SwiGLU gate projection ``dense_h_to_4h_gate`` (Llama shapes, C4)."""
+
+    def __init__(self, hidden_size: int, intermediate_size: int, config: Optional[TensorParallelConfig] = None,
+                 activation: Callable = F.gelu, *, gated: bool = False):
+        super().__init__()
+        self.config = config or TensorParallelConfig()
+        self.dense_h_to_4h = ColumnParallelLinear(hidden_size, intermediate_size, bias=True, config=self.config, gather_output=False)
+        self.dense_4h_to_h = RowParallelLinear(intermediate_size, hidden_size, bias=True, config=self.config, input_is_parallel=True)
+        self.dense_h_to_4h_gate = ColumnParallelLinear(hidden_size, intermediate_size, bias=True, config=self.config,
+                                                       gather_output=False) if gated else None
+        self.activation = activation
+        self.gated = gated
+        self._local_mlp = None  # test hook: fn(x, w_up, b_up, w_down, act, w_gate, b_gate) -> partial output
+
+    @classmethod
+    def from_dense(cls, w_up, b_up, w_down, b_down, config: TensorParallelConfig, activation: Callable = F.gelu,
+                   w_gate=None, b_gate=None) -> "TensorParallelMLP":
+        """Shard full (replicated) weights: rows of W_up / W_gate, columns of W_down (tensor_parallel.py:130-135, :249-254)."""
+        i, h = w_up.shape
+        m = cls(h, i, config, activation, gated=w_gate is not None).to(device=w_up.device, dtype=w_up.dtype)
+        m.dense_h_to_4h.load_full(w_up, b_up)
+        m.dense_4h_to_h.load_full(w_down, b_down)
+        if w_gate is not None:
+            m.dense_h_to_4h_gate.load_full(w_gate, b_gate)
+        return m
+
+    def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        act = "swiglu" if self.gated else activation_name(self.activation)
+        up, down, gate = self.dense_h_to_4h, self.dense_4h_to_h, self.dense_h_to_4h_gate
+        gw, gb = (gate.weight, gate.bias) if gate is not None else (None, None)
+        if self._local_mlp is not None:
+            partial = self._local_mlp(hidden_states, up.weight, up.bias, down.weight, act, gw, gb)
+        else:
+            from .. import ops
+            # the down bias must be added once, after the reduction (reference :304-308)
+            partial = ops.fused_mlp(hidden_states, up.weight, up.bias, down.weight, None, act, gw, gb)
+        if self.config.tp_size > 1:
+            comm.all_reduce(partial, group=self.config.get_tp_group())
+        return partial if down.bias is None else partial + down.bias
+
+
+class TensorParallelAttention(nn.Module):
+    """reference :403-599 — heads split across ranks (requires ``Hq % tp == 0``, :447-448), attention on the local heads,
+    row-parallel output projection (one all-reduce). ``num_kv_heads`` adds GQA (tp=8 with 8 KV heads -> 1 per rank)."""
+
+    def __init__(self, hidden_size: int, num_attention_heads: int, config: Optional[TensorParallelConfig] = None,
+                 attention_dropout: float = 0.1, is_cross_attention: bool = False, head_dim: Optional[int] = None, *,
+                 num_kv_heads: Optional[int] = None, causal: bool = False):
+        super().__init__()
+        self.config = config or TensorParallelConfig()
+        tp = self.config.tp_size
+        self.hidden_size = hidden_size
+        self.num_attention_heads = num_attention_heads
+        self.num_kv_heads = num_kv_heads or num_attention_heads
+        self.head_dim = head_dim or hidden_size // num_attention_heads
+        if num_attention_heads % tp != 0 or self.num_kv_heads % tp != 0:
+            raise ValueError(f"num_attention_heads ({num_attention_heads}) and num_kv_heads ({self.num_kv_heads}) must be "
+                             f"divisible by tp_size ({tp})")
+        self.heads_per_rank = num_attention_heads // tp
+        self.kv_heads_per_rank = self.num_kv_heads // tp
+        self.is_cross_attention = is_cross_attention
+        self.causal = causal
+        self.query = ColumnParallelLinear(hidden_size, num_attention_heads * self.head_dim, config=self.config, gather_output=False)
+        self.key = ColumnParallelLinear(hidden_size, self.num_kv_heads * self.head_dim, config=self.config, gather_output=False)
+        self.value = ColumnParallelLinear(hidden_size, self.num_kv_heads * self.head_dim, config=self.config, gather_output=False)
+        self.output = RowParallelLinear(num_attention_heads * self.head_dim, hidden_size, config=self.config, input_is_parallel=True)
+        self.dropout = nn.Dropout(attention_dropout)
+        self._local_attn = None  # test hook
+
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                encoder_hidden_states: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if attention_mask is not None:
+            raise NotImplementedError("additive attention masks are not supported on the CUDA path; use causal=True")
+        B, S, _ = hidden_states.shape
+        kv_src = encoder_hidden_states if (self.is_cross_attention and encoder_hidden_states is not None) else hidden_states
+        q = self.query(hidden_states).view(B, S, self.heads_per_rank, self.head_dim)
+        k = self.key(kv_src).view(B, kv_src.shape[1], self.kv_heads_per_rank, self.head_dim)
+        v = self.value(kv_src).view(B, kv_src.shape[1], self.kv_heads_per_rank, self.head_dim)
+        if self._local_attn is not None:
+            ctx = self._local_attn(q, k, v, self.causal)
+        else:
+            from .. import ops
+            ctx = ops.flash_attn_fwd(q, k, v, causal=self.causal)
+        return self.output(ctx.reshape(B, S, self.heads_per_rank * self.head_dim))
+
+
+class ModelParallelConverter:
+    """reference :617-798 — swaps ``*.mlp`` blocks made of two Linears (or gate/up/down) for ``TensorParallelMLP``,
+    sharding and COPYING the weights."""
+
+    def __init__(self, config: TensorParallelConfig):
+        self.config = config
+
+    def convert_model(self, model: nn.Module) -> nn.Module:
+        for name, sub in list(model.named_children()):
+            new = self._convert_module(sub)
+            if new is not None:
+                setattr(model, name, new)
+            else:
+                self.convert_model(sub)
+        return model
+
+    def _convert_module(self, m: nn.Module) -> Optional[nn.Module]:
+        if isinstance(m, (TensorParallelMLP, ColumnParallelLinear, RowParallelLinear)):
+            return None
+        if all(hasattr(m, a) for a in ("gate_proj", "up_proj", "down_proj")):
+            return TensorParallelMLP.from_dense(m.up_proj.weight, m.up_proj.bias, m.down_proj.weight, m.down_proj.bias,
+                                                self.config, F.silu, m.gate_proj.weight, m.gate_proj.bias)
+        if hasattr(m, "fc1") and hasattr(m, "fc2") and isinstance(m.fc1, nn.Linear):
+            act = getattr(m, "activation_fn", getattr(m, "act", F.gelu))
+            return TensorParallelMLP.from_dense(m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.config, act)
+        if hasattr(m, "c_fc") and hasattr(m, "c_proj"):  # GPT-2 Conv1D, weight [in, out]
+            act = getattr(m, "act", F.gelu)
+            return TensorParallelMLP.from_dense(m.c_fc.weight.t().contiguous(), m.c_fc.bias, m.c_proj.weight.t().contiguous(),
+                                                m.c_proj.bias, self.config, act)
+        return None

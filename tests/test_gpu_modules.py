@@ -1,0 +1,187 @@
+"""The reference-facing module API on a B200: each module's forward against the oracle composed with the same weights."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import attn_mlp_oracle as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu(built_lib):
+    assert torch.cuda.is_available()
+
+
+def rel(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    return ((got - ref).abs().mean() / ref.abs().mean().clamp_min(1e-12)).item(), (got - ref).abs().max().item()
+
+
+def test_flash_attention3_module_masks_and_dtypes():
+    from kernels.attention.flash_attention import FlashAttention3, FlashAttentionConfig
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v = (torch.randn(2, 200, 4, 64, device="cuda", generator=g) for _ in range(3))  # fp32 in, default precision fp16
+    fa = FlashAttention3(FlashAttentionConfig(causal=True))
+    o = fa(q, k, v)
+    assert o.dtype == torch.float32  # output dtype = input dtype (reference :222-225)
+    ro, _ = orc.attention_ref(q.half().cpu(), k.half().cpu(), v.half().cpu(), causal=True)
+    assert rel(o, ro)[1] < 5e-3
+    mask = torch.ones(2, 200, device="cuda")
+    mask[1, 150:] = 0
+    o2 = FlashAttention3(FlashAttentionConfig(precision="bf16"))(q, k, v, mask)
+    ro2, _ = orc.attention_ref(q.bfloat16().cpu(), k.bfloat16().cpu(), v.bfloat16().cpu(),
+                               kv_lens=torch.tensor([200, 150], dtype=torch.int32))
+    assert rel(o2, ro2)[1] < 2e-2
+    with pytest.raises(NotImplementedError):
+        fa(q, k, v, torch.ones(2, 200, 200, device="cuda"))
+    with pytest.raises(NotImplementedError):
+        FlashAttention3(FlashAttentionConfig(precision="fp8"))(q, k, v)
+
+
+@pytest.mark.parametrize("cls_name", ["FlashAttentionLayer", "FlashSelfAttention"])
+def test_attention_layers_vs_oracle(cls_name):
+    import kernels.attention.flash_attention as fa
+
+    torch.manual_seed(0)
+    hidden, H, Hkv, B, S = 512, 8, 2, 2, 320
+    layer = getattr(fa, cls_name)(hidden, H, fa.FlashAttentionConfig(causal=True, precision="bf16"), num_kv_heads=Hkv)
+    layer = layer.to("cuda", torch.bfloat16).eval()
+    x = torch.randn(B, S, hidden, device="cuda", dtype=torch.bfloat16)
+    y = layer(x)
+    D = hidden // H
+    with torch.no_grad():
+        if cls_name == "FlashAttentionLayer":
+            q, k, v = layer.q_proj(x), layer.k_proj(x), layer.v_proj(x)
+        else:
+            q, k, v = layer.qkv_proj(x).split([hidden, Hkv * D, Hkv * D], dim=-1)
+        ctx, _ = orc.attention_ref(q.view(B, S, H, D).cpu(), k.view(B, S, Hkv, D).cpu(), v.view(B, S, Hkv, D).cpu(), causal=True)
+        ref = F.linear(ctx.reshape(B, S, hidden), layer.o_proj.weight.float().cpu(), layer.o_proj.bias.float().cpu())
+    mr, mx = rel(y, ref)
+    assert mr < 1e-2 and mx < 2e-2
+
+
+def test_paged_decode_branch_and_functional_shims():
+    from kernels.attention.flash_attention import FlashAttentionConfig, FlashAttentionLayer
+    from kernels.triton.attention_kernels import triton_paged_attention_forward, triton_reshape_and_cache
+
+    torch.manual_seed(0)
+    hidden, H, Hkv, B, bs, L, nblk = 512, 8, 4, 3, 16, 2, 48
+    D = hidden // H
+    layer = FlashAttentionLayer(hidden, H, FlashAttentionConfig(precision="bf16"), num_kv_heads=Hkv).to("cuda", torch.bfloat16).eval()
+    kc = torch.randn(nblk, L, bs, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    vc = torch.randn(nblk, L, bs, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    lens = torch.tensor([40, 17, 160], device="cuda", dtype=torch.int32)
+    tables = torch.randperm(nblk)[:B * 10].view(B, 10).to("cuda", torch.int32)
+    x = torch.randn(B, 1, hidden, device="cuda", dtype=torch.bfloat16)
+    # the model's loop: project k,v of the new token, append, then attend (reference baseline/model_utils.py:658-751)
+    with torch.no_grad():
+        k_new = layer.k_proj(x).view(B, 1, Hkv, D)
+        v_new = layer.v_proj(x).view(B, 1, Hkv, D)
+    rk, rv = kc.cpu().clone(), vc.cpu().clone()
+    triton_reshape_and_cache(k_new, v_new, kc, vc, tables, lens, 1)
+    orc.kv_append_ref(k_new[:, 0].cpu(), v_new[:, 0].cpu(), rk, rv, lens.cpu(), tables.cpu(), 1)
+    assert torch.equal(kc.cpu(), rk) and torch.equal(vc.cpu(), rv)
+    y = layer(x, physical_kv_cache_k=kc, physical_kv_cache_v=vc, block_tables=tables, context_lengths=lens,
+              kv_cache_block_size=bs, max_seq_len=160, layer_idx=1)
+    with torch.no_grad():
+        q = layer.q_proj(x).view(B, H, D)
+        ctx, _ = orc.decode_attention_ref(q.cpu(), rk, rv, lens.cpu(), block_tables=tables.cpu(), layer_idx=1)
+        ref = F.linear(ctx.reshape(B, 1, hidden), layer.o_proj.weight.float().cpu(), layer.o_proj.bias.float().cpu())
+    assert rel(y, ref)[1] < 2e-2
+    # functional form writes into `output` in place
+    qf = q.view(B, H, 1, D).contiguous()
+    out = torch.empty_like(qf)
+    triton_paged_attention_forward(qf, out, kc, vc, tables, lens, bs, 160, 1)
+    assert rel(out.view(B, H, D), ctx)[1] < 2e-2
+    with pytest.raises(ValueError):
+        layer(x, block_tables=tables)  # missing paged arguments (reference :583-586)
+
+
+def test_fused_mlp_modules_load_reference_state_dicts(golden_dir):
+    from kernels.mlp.fused_mlp import FusedMLP, FusedMLPConfig, FusedTransformerMLP
+
+    vecs = torch.load(os.path.join(golden_dir, "mlp_reference_vectors.pt"))
+    for act in ("gelu", "relu", "swiglu"):
+        d = vecs[f"FusedTransformerMLP_{act}"]
+        mod = FusedTransformerMLP(d["hidden"], d["intermediate"], act, FusedMLPConfig(precision="bf16"))
+        mod.load_state_dict(d["state_dict"])  # the reference's own state-dict keys
+        y = mod.to("cuda")(d["x"].to("cuda"))  # fp32 in -> bf16 compute -> fp32 out
+        assert y.dtype == torch.float32
+        mr, mx = rel(y, d["y"])
+        assert mr < 2e-2 and mx < 2e-2, (act, mr, mx)
+    d = vecs["FusedMLP_gelu_erf"]
+    mod = FusedMLP(d["hidden"], d["intermediate"], FusedMLPConfig(activation_fn="gelu", precision="bf16"))
+    mod.load_state_dict(d["state_dict"])
+    assert rel(mod.to("cuda")(d["x"].to("cuda")), d["y"])[1] < 2e-2
+
+
+def test_functional_mlp_and_attention_shims():
+    from kernels.triton.attention_kernels import triton_ring_attention_forward
+    from kernels.triton.flash_attention_kernels import triton_flash_attention
+    from kernels.triton.mlp_kernels import pytorch_fused_mlp, triton_fused_mlp
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).to(torch.bfloat16)
+    x, w1, b1, w2, b2 = r(2, 50, 256), r(512, 256, sc=0.05), r(512, sc=0.1), r(256, 512, sc=0.05), r(256, sc=0.1)
+    c = lambda t: t.cpu()
+    y_t = triton_fused_mlp(x, w1, b1, w2, b2, "gelu")
+    y_p = pytorch_fused_mlp(x, w1, b1, w2, b2, "gelu")
+    assert rel(y_t, orc.mlp_ref(c(x), c(w1), c(b1), c(w2), c(b2), "gelu_tanh"))[1] < 2e-2
+    assert rel(y_p, orc.mlp_ref(c(x), c(w1), c(b1), c(w2), c(b2), "gelu"))[1] < 2e-2
+    q, k, v = r(2, 4, 300, 64), r(2, 4, 300, 64), r(2, 4, 300, 64)  # [B,H,S,D]
+    o = triton_ring_attention_forward(q, k, v)
+    ro, _ = orc.attention_ref(c(q).transpose(1, 2), c(k).transpose(1, 2), c(v).transpose(1, 2))
+    assert o.shape == (2, 300, 256) and rel(o, ro.reshape(2, 300, 256))[1] < 2e-2
+    o2, lse = triton_flash_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=True, return_softmax=True)
+    ro2, rl = orc.attention_ref(c(q).transpose(1, 2), c(k).transpose(1, 2), c(v).transpose(1, 2), causal=True)
+    assert rel(o2, ro2)[1] < 2e-2 and (lse.cpu() - rl).abs().max() < 1e-2
+
+
+def test_ring_module_single_gpu_equals_dense():
+    from kernels.attention.ring_attention import RingAttentionConfig, RingSelfAttention
+
+    torch.manual_seed(0)
+    mod = RingSelfAttention(512, 8, RingAttentionConfig(), causal=True).to("cuda", torch.bfloat16).eval()
+    x = torch.randn(2, 384, 512, device="cuda", dtype=torch.bfloat16)
+    y = mod(x)
+    with torch.no_grad():
+        q, k, v = mod.qkv_proj(x).split(512, dim=-1)
+        ctx, _ = orc.attention_ref(*(t.view(2, 384, 8, 64).cpu() for t in (q, k, v)), causal=True)
+        ref = F.linear(ctx.reshape(2, 384, 512), mod.out_proj.weight.float().cpu(), mod.out_proj.bias.float().cpu())
+    assert rel(y, ref)[1] < 2e-2
+
+
+def test_optimizer_on_hf_gpt2_matches_eager_and_generates():
+    """BASELINE config 1/2 path: HF GPT-2 (random init, GPT-2-small widths, 2 layers) through Optimizer.optimize vs the HF
+    eager model — logits within the reference's own logits tolerance (verify_baseline.py:125 rtol=atol=1e-2 is for
+    fp32-vs-fp32; bf16 storage gets 5e-2 here, well inside test_parallelism.py:322's 0.1)."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from ml_inference_optimizer import Optimizer
+
+    torch.manual_seed(0)
+    cfg = GPT2Config(n_layer=2, attn_implementation="eager")
+    eager = GPT2LMHeadModel(cfg).eval()
+    ids = torch.randint(0, cfg.vocab_size, (2, 192))
+    with torch.no_grad():
+        ref = eager(ids).logits
+    import copy
+
+    model = copy.deepcopy(eager).to("cuda", torch.bfloat16)
+    opt = Optimizer(model)
+    optimized = opt.optimize(use_flash_attention=True, use_fused_mlp=True, tensor_parallel_size=1)
+    assert opt.applied == {"flash_attention": True, "fused_mlp": True}
+    with torch.no_grad():
+        got = optimized(ids.cuda()).logits
+    assert (got.float().cpu() - ref).abs().max().item() < 5e-2
+    # greedy generation through the HF cache protocol: cached decode must agree with re-running the full prefix
+    out = optimized.generate(input_ids=ids[:1, :64], max_new_tokens=8)
+    assert out.shape == (1, 72)
+    with torch.no_grad():
+        full = optimized(out[:, :-1]).logits[:, -1]
+    assert full.argmax(-1).item() == out[0, -1].item() or \
+        (full.float().topk(2).values[0, 0] - full.float().topk(2).values[0, 1]).item() < 5e-2

@@ -1,0 +1,181 @@
+"""CPU checks of the host-side mirror of the reference API: signatures, validation, model surgery (weights copied),
+mask lowering, partition helpers. No kernel runs here."""
+import inspect
+import math
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from kernels.attention.flash_attention import (FlashAttention3, FlashAttentionConfig, FlashAttentionLayer, FlashSelfAttention,
+                                               ModelConverter, key_padding_mask_to_lengths)
+from kernels.attention.ring_attention import RingAttentionConfig, RingCrossAttention, RingSelfAttention, calculate_theoretical_flops
+from kernels.mlp.fused_mlp import (FusedMLP, FusedMLPConfig, FusedMLPGeluTanh, FusedMLPReLU, FusedMLPSwiGLU, FusedTransformerMLP,
+                                   MLPConverter)
+from ml_inference_optimizer import Optimizer
+from parallelism import communication as comm
+from parallelism.sequence_parallel import SequenceParallelConfig
+from parallelism.tensor_parallel import TensorParallelConfig, TensorParallelMLP, activation_name
+
+
+def test_signatures_match_reference_appendix_a():
+    assert list(inspect.signature(FlashAttentionConfig).parameters) == [
+        "block_size", "causal", "softmax_scale", "dropout_p", "return_softmax", "use_triton", "memory_efficient", "precision",
+        "normalize_query", "fp8_ortho_matrix"]
+    assert list(inspect.signature(FlashAttention3.forward).parameters) == ["self", "q", "k", "v", "mask"]
+    assert list(inspect.signature(FlashAttentionLayer.__init__).parameters) == [
+        "self", "hidden_size", "num_attention_heads", "config", "num_kv_heads"]
+    assert list(inspect.signature(FusedMLPConfig).parameters) == [
+        "activation_fn", "dropout_prob", "use_triton", "precision", "fuse_bias_gelu", "recompute_activation",
+        "sequence_parallel", "tensor_parallel", "checkpoint_activation"]
+    assert list(inspect.signature(FusedTransformerMLP.__init__).parameters) == [
+        "self", "hidden_size", "intermediate_size", "activation_fn", "config"]
+    assert list(inspect.signature(Optimizer.optimize).parameters) == [
+        "self", "use_flash_attention", "use_fused_mlp", "tensor_parallel_size"]
+    assert list(inspect.signature(RingAttentionConfig).parameters)[:4] == ["world_size", "chunk_size", "fuse_qkv", "use_flash_attention"]
+    from kernels.triton.attention_kernels import triton_paged_attention_forward, triton_reshape_and_cache
+    assert list(inspect.signature(triton_paged_attention_forward).parameters) == [
+        "query", "output", "k_cache", "v_cache", "block_tables", "context_lengths", "block_size", "max_seq_len", "layer_idx"]
+    assert list(inspect.signature(triton_reshape_and_cache).parameters) == [
+        "key", "value", "k_cache", "v_cache", "block_tables", "context_lengths", "layer_idx"]
+    from kernels.triton.mlp_kernels import triton_fused_mlp
+    assert list(inspect.signature(triton_fused_mlp).parameters) == [
+        "hidden_states", "fc1_weight", "fc1_bias", "fc2_weight", "fc2_bias", "activation", "fc1_gate_weight", "fc1_gate_bias"]
+    assert list(inspect.signature(comm.all_reduce).parameters) == [
+        "tensor", "op", "async_op", "group", "use_fp16", "use_bf16", "use_unbalanced", "stream"]
+
+
+def test_config_validation():
+    with pytest.raises(ValueError):
+        FlashAttentionConfig(precision="int8")
+    with pytest.raises(ValueError):
+        RingAttentionConfig(world_size=0)
+    with pytest.raises(ValueError):
+        RingAttentionConfig(attention_dropout=1.0)
+    with pytest.raises(ValueError):
+        SequenceParallelConfig(world_size=4, sp_size=3)
+    with pytest.raises(ValueError):
+        SequenceParallelConfig(attention_handling="ulysses")
+    with pytest.raises(AssertionError):
+        TensorParallelConfig(world_size=4, tp_size=3)
+    with pytest.raises(ValueError):
+        FlashAttentionLayer(100, 3)
+
+
+def test_module_attribute_names_and_shapes():
+    layer = FlashAttentionLayer(256, 8, num_kv_heads=2)
+    assert layer.k_proj.out_features == 2 * 32 and layer.q_proj.bias is not None
+    fused = FlashSelfAttention(256, 8, num_kv_heads=2)
+    assert fused.qkv_proj.out_features == 256 + 2 * 2 * 32
+    assert set(dict(FusedMLPSwiGLU(64, 128).named_parameters())) == {
+        "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc1_gate.weight", "fc1_gate.bias"}
+    assert isinstance(FusedTransformerMLP(64, 128, "gelu").mlp, FusedMLPGeluTanh)
+    assert isinstance(FusedTransformerMLP(64, 128, "relu").mlp, FusedMLPReLU)
+    assert FusedMLP(64, 128, FusedMLPConfig(activation_fn="gelu"))._activation() == "gelu_erf"
+    assert FusedTransformerMLP(64, 128, "gelu").mlp._activation() == "gelu_tanh"
+    ring = RingSelfAttention(128, 4, RingAttentionConfig())
+    assert ring.qkv_proj.out_features == 384 and hasattr(ring, "out_proj")
+    assert hasattr(RingCrossAttention(128, 4, RingAttentionConfig()), "k_proj")
+    tp = TensorParallelMLP(64, 256)
+    assert tp.dense_h_to_4h.weight.shape == (256, 64) and tp.dense_4h_to_h.weight.shape == (64, 256)
+
+
+def test_no_cpu_fallback_in_modules():
+    with pytest.raises(ValueError, match="CUDA"):
+        FlashAttention3()(torch.randn(1, 8, 2, 64), torch.randn(1, 8, 2, 64), torch.randn(1, 8, 2, 64))
+    with pytest.raises(ValueError, match="CUDA"):
+        FusedTransformerMLP(64, 128)(torch.randn(1, 8, 64))
+
+
+def test_key_padding_mask_lowering():
+    m = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1]])
+    assert key_padding_mask_to_lengths(m, 5).tolist() == [3, 5]
+    assert key_padding_mask_to_lengths(m.unsqueeze(1).bool(), 5).tolist() == [3, 5]
+    with pytest.raises(NotImplementedError):
+        key_padding_mask_to_lengths(torch.tensor([[0, 1, 1, 1, 1]]), 5)  # left padding
+    with pytest.raises(NotImplementedError):
+        key_padding_mask_to_lengths(torch.ones(1, 5, 5), 5)  # dense mask
+
+
+def test_activation_mapping():
+    assert activation_name(F.gelu) == "gelu_erf"
+    assert activation_name(nn.GELU(approximate="tanh")) == "gelu_tanh"
+    assert activation_name(F.relu) == "relu"
+    assert activation_name(F.silu) == "swiglu"
+    with pytest.raises(ValueError):
+        activation_name(torch.tanh)
+
+
+def test_converters_copy_weights_gpt2():
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    torch.manual_seed(0)
+    cfg = GPT2Config(n_layer=2, n_head=4, n_embd=128, vocab_size=256, n_positions=64)
+    model = GPT2LMHeadModel(cfg).eval()
+    ref_attn = model.transformer.h[0].attn
+    ref_mlp = model.transformer.h[0].mlp
+    c_attn_w, c_fc_w, c_proj_b = ref_attn.c_attn.weight.clone(), ref_mlp.c_fc.weight.clone(), ref_mlp.c_proj.bias.clone()
+    ModelConverter(FlashAttentionConfig(causal=True, precision="bf16")).convert_model(model)
+    MLPConverter().convert_model(model)
+    new_attn = model.transformer.h[0].attn.inner
+    new_mlp = model.transformer.h[0].mlp.inner.mlp
+    assert isinstance(new_attn, FlashSelfAttention) and new_attn.config.causal
+    assert torch.equal(new_attn.qkv_proj.weight, c_attn_w.t())  # Conv1D stores [in, out]
+    assert isinstance(new_mlp, FusedMLPGeluTanh)  # gelu_new -> tanh GELU
+    assert torch.equal(new_mlp.fc1.weight, c_fc_w.t()) and torch.equal(new_mlp.fc2.bias, c_proj_b)
+    assert model.transformer.h[0].attn.layer_idx == 0 and model.transformer.h[1].attn.layer_idx == 1
+
+
+def test_mlp_converter_llama_style_and_load_from_standard():
+    class LlamaMLP(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj, self.up_proj = nn.Linear(32, 96, bias=False), nn.Linear(32, 96, bias=False)
+            self.down_proj = nn.Linear(96, 32, bias=False)
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mlp = LlamaMLP()
+
+    blk = Block()
+    gate_w = blk.mlp.gate_proj.weight.clone()
+    MLPConverter().convert_model(blk)
+    fused = blk.mlp.inner.mlp
+    assert isinstance(fused, FusedMLPSwiGLU) and torch.equal(fused.fc1_gate.weight, gate_w)
+    assert torch.count_nonzero(fused.fc1.bias) == 0  # missing biases become zeros (reference fused_mlp.py:549-555)
+    t = FusedTransformerMLP(32, 96, "swiglu")
+    sd = {"x.gate_proj.weight": torch.randn(96, 32), "x.up_proj.weight": torch.randn(96, 32), "x.down_proj.weight": torch.randn(32, 96)}
+    t.load_from_standard_mlp(sd, prefix="x.")
+    assert torch.equal(t.mlp.fc1_gate.weight, sd["x.gate_proj.weight"]) and torch.equal(t.mlp.fc2.weight, sd["x.down_proj.weight"])
+
+
+def test_sequence_partition_roundtrip_single_process():
+    x = torch.arange(2 * 16 * 3, dtype=torch.float32).view(2, 16, 3)
+    for part in ("contiguous", "zigzag"):
+        shards = [comm.scatter_along_sequence_dim(x, 4, partition=part, rank=r) for r in range(4)]
+        assert all(s.shape == (2, 4, 3) for s in shards)
+        if part == "zigzag":  # rank 0 owns chunks 0 and 7
+            assert torch.equal(shards[0], torch.cat([x[:, 0:2], x[:, 14:16]], dim=1))
+        covered = torch.cat(shards, dim=1)
+        assert sorted(covered[0, :, 0].tolist()) == x[0, :, 0].tolist()
+    with pytest.raises(ValueError):
+        comm.scatter_along_sequence_dim(x[:, :15], 4, rank=0)
+
+
+def test_flops_formula_and_memory_model():
+    assert calculate_theoretical_flops(128, 2, 64, 4) == 3 * 2 * 128 * 64 * 64 + 2 * (2 * 4 * 128 * 128 * 16) + 2 * 128 * 64 * 64
+    mem = FlashAttention3().get_theoretical_memory_usage(4096, 8, 12, 64)
+    assert mem["memory_reduction_factor"] > 10
+
+
+def test_optimizer_profile_and_cpu_refusal():
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    model = GPT2LMHeadModel(GPT2Config(n_layer=1, n_head=2, n_embd=64, vocab_size=128, n_positions=32))
+    opt = Optimizer(model)
+    prof = opt.profile()
+    assert prof["attention_modules"] == ["transformer.h.0.attn"] and prof["mlp_modules"] == ["transformer.h.0.mlp"]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.optimize()
