@@ -1,0 +1,83 @@
+"""Multi-GPU parity check, one rank per GPU over NCCL (launched by tests/test_multi_gpu.py or by hand):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py
+
+Ring attention (contiguous + zigzag, causal + non-causal, GQA) and tensor-parallel MLP / attention against the fp32
+oracle on the full problem."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oracle import attn_mlp_oracle as orc
+    from parallelism import communication as comm
+    from parallelism import parallel_utils as pu
+    from parallelism.ring import ring_attention_forward
+    from parallelism.tensor_parallel import TensorParallelAttention, TensorParallelConfig, TensorParallelMLP
+
+    ok = True
+    g = torch.Generator().manual_seed(0)
+    B, S, Hq, Hkv, D = 2, 256 * world, 8, 2, 128
+    q, k, v = torch.randn(B, S, Hq, D, generator=g), torch.randn(B, S, Hkv, D, generator=g), torch.randn(B, S, Hkv, D, generator=g)
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    for causal in (False, True):
+        full, lse_full = orc.attention_ref(q, k, v, causal=causal)
+        for part in ("contiguous", "zigzag"):
+            sh = lambda t: comm.scatter_along_sequence_dim(t, world, partition=part, rank=rank).contiguous().to(dev)
+            o, lse = ring_attention_forward(sh(q), sh(k), sh(v), causal=causal, partition=part, return_lse=True)
+            want = comm.scatter_along_sequence_dim(full, world, partition=part, rank=rank)
+            want_lse = comm.scatter_along_sequence_dim(lse_full.transpose(1, 2), world, partition=part, rank=rank).transpose(1, 2)
+            e_o = (o.float().cpu() - want).abs().max().item()
+            e_l = (lse.cpu() - want_lse).abs().max().item()
+            good = e_o <= 2e-2 and e_l <= 1e-2
+            ok &= good
+            print(f"[rank {rank}] ring causal={causal} {part}: max|dO|={e_o:.2e} max|dLSE|={e_l:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # tensor-parallel MLP (SwiGLU, Llama-style) and attention
+    pu.initialize_tensor_parallel(world)
+    cfg = TensorParallelConfig(world_size=world, tp_size=world)
+    g = torch.Generator().manual_seed(1)
+    h, i, T = 512, 1024 * world, 300
+    r = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).bfloat16()
+    x, wu, bu, wg, bg, wd, bd = r(T, h), r(i, h, sc=0.03), r(i, sc=0.1), r(i, h, sc=0.03), r(i, sc=0.1), r(h, i, sc=0.03), r(h, sc=0.1)
+    c = lambda t: t.to(dev)
+    for name, act, gate in (("gelu", F.gelu, (None, None)), ("swiglu", F.silu, (wg, bg))):
+        m = TensorParallelMLP.from_dense(c(wu), c(bu), c(wd), c(bd), cfg, act, *(None if t is None else c(t) for t in gate))
+        y = m(c(x))
+        ref = orc.mlp_ref(x, wu, bu, wd, bd, "swiglu" if gate[0] is not None else "gelu", *gate)
+        e = (y.float().cpu() - ref).abs().max().item()
+        good = e <= 3e-2
+        ok &= good
+        print(f"[rank {rank}] tp mlp {name}: max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    torch.manual_seed(5)  # same weights on every rank, then sharded
+    H, Hk, Dh, hid = 8, 2 * world if world <= 4 else 8, 64, 512
+    attn = TensorParallelAttention(hid, H, cfg, attention_dropout=0.0, num_kv_heads=Hk, causal=True)
+    wq, wk, wv, wo = r(H * Dh, hid, sc=0.03), r(Hk * Dh, hid, sc=0.03), r(Hk * Dh, hid, sc=0.03), r(hid, H * Dh, sc=0.03)
+    attn = attn.to(dev, torch.bfloat16)
+    attn.query.load_full(c(wq)); attn.key.load_full(c(wk)); attn.value.load_full(c(wv)); attn.output.load_full(c(wo))
+    xs = r(2, 200, hid)
+    y = attn(c(xs))
+    qf, kf, vf = F.linear(xs.float(), wq.float()), F.linear(xs.float(), wk.float()), F.linear(xs.float(), wv.float())
+    ctx, _ = orc.attention_ref(qf.view(2, 200, H, Dh), kf.view(2, 200, Hk, Dh), vf.view(2, 200, Hk, Dh), causal=True)
+    ref = F.linear(ctx.reshape(2, 200, H * Dh), wo.float())
+    e = (y.float().cpu() - ref).abs().max().item()
+    good = e <= 3e-2
+    ok &= good
+    print(f"[rank {rank}] tp attention (Hq={H}, Hkv={Hk}): max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
