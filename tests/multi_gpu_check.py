@@ -55,7 +55,7 @@ def main():
         y = m(c(x))
         ref = orc.mlp_ref(x, wu, bu, wd, bd, "swiglu" if gate[0] is not None else "gelu", *gate)
         e = (y.float().cpu() - ref).abs().max().item()
-        good = e <= 3e-2
+        good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
         ok &= good
         print(f"[rank {rank}] tp mlp {name}: max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
     torch.manual_seed(5)  # same weights on every rank, then sharded
