@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in _existing_sources():
         obj = obj_dir / (src.stem + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split(), "-c", str(src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

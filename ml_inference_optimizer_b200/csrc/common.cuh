@@ -89,7 +89,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // GPU hang. try_wait suspends for a HW time slice per call, so the bound is minutes of wall time
 // only in the deadlock case and costs nothing otherwise.
 #ifndef B200_MBAR_SPIN_LIMIT
-#define B200_MBAR_SPIN_LIMIT (1u << 26)
+#define B200_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);

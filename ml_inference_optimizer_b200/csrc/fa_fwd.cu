@@ -22,12 +22,40 @@
 namespace b200 {
 namespace fa {
 
+#ifdef B200_FA_TRACE
+// developer instrumentation (never compiled into the product library): per-iteration clock64 stamps of one CTA
+__device__ long long* g_trace = nullptr;
+#define FA_TRACE_ON (g_trace != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0)
+#define FA_STAMP(slot, j, k) do { if (FA_TRACE_ON && (j) < 64) g_trace[((slot) * 64 + (j)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define FA_STAMP(slot, j, k) do {} while (0)
+#endif
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 128;
 constexpr int NUM_THREADS = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, safe for bf16/fp16 P and fp32 sums
+
+// 2^x for a pair of values on the FMA pipe (no MUFU): Cody-Waite range reduction with the 1.5*2^23 rounding constant,
+// degree-3 minimax polynomial on [-0.5, 0.5] (max rel. error 7.5e-5, far below the 2^-9 rounding of the 16-bit P),
+// exponent re-inserted with an integer add. Half of the exponentials of a tile go this way so the 16-lane/clk
+// MUFU pipe is not the bound of the softmax (the same idea as FlashAttention-4's software exp2).
+__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 j = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(j, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 pl = __ffma2_rn(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  pl = __ffma2_rn(pl, f, make_float2(0.6932609677f, 0.6932609677f));
+  pl = __ffma2_rn(pl, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(j.x) << 23));
+  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(j.y) << 23));
+  return r;
+}
 
 template <int D>
 struct Cfg {
@@ -80,8 +108,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* kv_full = q_full + 2;                                          // [NS]
   uint64_t* kv_empty = kv_full + NS;                                       // [NS]
   uint64_t* s_full = kv_empty + NS;                                        // [2]  MMA -> softmax
-  uint64_t* p_full = s_full + 2;                                           // [2]  softmax -> MMA (128 arrivals)
-  uint64_t* pv_done = p_full + 2;                                          // [2]  MMA -> softmax (O_t updated)
+  uint64_t* p_half = s_full + 2;                                           // [2][2] softmax -> MMA: P columns [0,64) / [64,128) stored (one arrival per warp)
+  uint64_t* pv_done = p_half + 4;                                          // [2]  MMA -> softmax (O_t updated)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform
@@ -109,7 +137,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_half[2 * i], 4);
+      mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&pv_done[i], 1);
     }
     for (int i = 0; i < NS; ++i) {
@@ -189,17 +218,20 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int t, int v_stage, bool accumulate) {
+      // P V for keys [64*part, 64*part+64) of the tile: issued as soon as that half of P is in TMEM, so the tensor
+      // pipe works on the first half while the softmax warps still exponentiate the second
+      auto issue_pv = [&](int t, int v_stage, int part, bool accumulate) {
         const uint64_t vd = vdesc0 + static_cast<uint64_t>(v_stage * TILE16);
         const uint32_t d_tmem = tmem_base + C::TMEM_O + static_cast<uint32_t>(t * D);
         const uint32_t p_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128) + C::TMEM_P_OFF;
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BLOCK_N / 16; ++ks) {
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int ks = part * 4 + k4;
             umma_ts(d_tmem, p_tmem + ks * 8, vd + static_cast<uint64_t>(ks * 128), idesc_pv,
                     (accumulate || ks > 0) ? 1u : 0u);
           }
-          umma_commit(&pv_done[t]);
+          if (part == 1) umma_commit(&pv_done[t]);
         }
         __syncwarp();
       };
@@ -233,9 +265,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         for (int t = 0; t < 2; ++t) {
           const int nt_t = t == 0 ? n0 : n1;
           if (j < nt_t) {
-            mbar_wait(&p_full[t], static_cast<uint32_t>(j & 1));
+            if (lane == 0) FA_STAMP(2 + t, j, 0);
+            mbar_wait(&p_half[2 * t], static_cast<uint32_t>(j & 1));
             tc_fence_after();
-            issue_pv(t, v_stage, j > 0);
+            if (lane == 0) FA_STAMP(2 + t, j, 1);
+            issue_pv(t, v_stage, 0, j > 0);
+            mbar_wait(&p_half[2 * t + 1], static_cast<uint32_t>(j & 1));
+            tc_fence_after();
+            issue_pv(t, v_stage, 1, true);
+            if (lane == 0) FA_STAMP(2 + t, j, 2);
           }
           if (j + 1 < nt_t) {
             if (!next_k_ready) {
@@ -244,6 +282,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
               next_k_ready = true;
             }
             issue_qk(t, k_stage);
+            if (lane == 0) FA_STAMP(2 + t, j, 3);
           }
         }
         release(v_stage);
@@ -276,12 +315,14 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&s_full[t], static_cast<uint32_t>(j & 1));
       tc_fence_after();
+      if (wg_tid == 0) FA_STAMP(t, j, 0);
       uint32_t s[128];
       tmem_ld_x32(tS + 0, s + 0);
       tmem_ld_x32(tS + 32, s + 32);
       tmem_ld_x32(tS + 64, s + 64);
       tmem_ld_x32(tS + 96, s + 96);
       tmem_wait_ld();
+      if (wg_tid == 0) FA_STAMP(t, j, 1);
       // ---- masking: keys >= limit (relative to the tile) are invisible ----
       const int kv0 = j * BLOCK_N;
       int limit = kv_len - kv0;
@@ -304,6 +345,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
       }
       const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      if (wg_tid == 0) FA_STAMP(t, j, 2);
       // ---- lazy rescale decision ----
       float alpha = 1.0f;
       bool rescale = false;
@@ -329,28 +371,53 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           tmem_st_x32(tO + c * 32, o);
         }
       }
-      // ---- P = exp2(s * scale - m_used), row sum, pack to 16 bit, store to TMEM ----
+      // ---- P = exp2(s * scale - m_used), row sum, pack to 16 bit, store to TMEM (two halves of 64 keys) ----
       const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
-      const float neg_m = -m_ref;
-      float sum0 = 0.f, sum1 = 0.f;
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nm2 = make_float2(-m_ref, -m_ref);
+      float2 sum2 = make_float2(0.f, 0.f);
+      uint32_t pk0[32], pk1[32];
+      // columns c, c+1; packed fp32x2 FMA / ADD halve the issue slots. `poly` pairs use the FMA-pipe exp2.
+      auto exp_pair = [&](int c, bool poly) -> uint32_t {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
+        const float2 e = poly ? poly_exp2_pair(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        sum2 = __fadd2_rn(sum2, e);
+        return Pack2<T>::pack(e.x, e.y);
+      };
+      auto publish = [&](int half) {
+        tmem_wait_st();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_half[2 * t + half]);
+      };
+      // warp-uniform choice: tcgen05.st / the barrier arrive below are warp-collective
+      if (!__any_sync(0xffffffffu, limit < BLOCK_N)) {
+        // unmasked tile (the common case): every other pair on the FMA pipe
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[32];
+        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i, (i & 1) != 0);
+        tmem_st_x32(tP, pk0);
+        if (wg_tid == 0) FA_STAMP(t, j, 3);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int c = half * 64 + i * 2;
-          const float e0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2, neg_m));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2, neg_m));
-          sum0 += e0;
-          sum1 += e1;
-          pk[i] = Pack2<T>::pack(e0, e1);
-        }
-        tmem_st_x32(tP + half * 32, pk);
+        for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i, (i & 1) != 0);
+        if (wg_tid == 0) FA_STAMP(t, j, 4);
+        publish(0);  // the first half of P has landed: its P V MMAs start while we finish the row
+        if (wg_tid == 0) FA_STAMP(t, j, 5);
+#pragma unroll
+        for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i, (i & 1) != 0);
+        tmem_st_x32(tP + 32, pk1);
+      } else {
+        // masked tile (diagonal / ragged tail): MUFU only, so exp2(-inf) is exactly 0
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i, false);
+        tmem_st_x32(tP, pk0);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i, false);
+        publish(0);
+        tmem_st_x32(tP + 32, pk1);
       }
-      l_run += sum0 + sum1;
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      l_run += sum2.x + sum2.y;
+      if (wg_tid == 0) FA_STAMP(t, j, 6);
+      publish(1);
+      if (wg_tid == 0) FA_STAMP(t, j, 7);
     }
 
     // ---- epilogue: O / l -> 16 bit -> smem (128B swizzle) -> TMA store; LSE -> global ----
@@ -443,6 +510,12 @@ static int make_bshd_tmap(CUtensorMap* out, const void* base, int B, int S, int 
 
 }  // namespace fa
 }  // namespace b200
+
+#ifdef B200_FA_TRACE
+extern "C" int b200_debug_fa_trace(long long* dev_buf) {
+  return cudaMemcpyToSymbol(b200::fa::g_trace, &dev_buf, sizeof(dev_buf)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Sq, int Sk,
                            int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3],

@@ -172,7 +172,7 @@ def _fa_case(B, Sq, Sk, Hq, Hkv, D, causal, offset=0, kv_lens=None, seed=0, dtyp
     ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=causal, causal_offset=offset,
                                kv_lens=None if lens is None else lens.cpu())
     name = f"fa B{B} Sq{Sq} Sk{Sk} Hq{Hq} Hkv{Hkv} D{D} causal={causal} off={offset} lens={kv_lens} {dtype}"
-    a, diff = _stats(name + " O", o, ro, 2e-2, 1e-2)
+    a, diff = _stats(name + " O", o, ro, 2e-2, 3e-2)
     lse_c, rl_c = lse.cpu(), rl
     both_inf = torch.isinf(lse_c) & torch.isinf(rl_c) & (lse_c < 0) & (rl_c < 0)
     b, dl = _stats(name + " LSE", torch.where(both_inf, torch.zeros_like(lse_c), lse_c),
