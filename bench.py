@@ -60,7 +60,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons. The sampler is started before the warm-up (nvidia-smi needs a moment to
+    start); only samples whose arrival time falls inside [t_start, t_end] of the timed region are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -69,7 +70,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -78,32 +79,42 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, smax, reasons, power = [], [], set(), []
+            for _, ln in rows:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, smax, reasons, power
+
+        inside = [(t, l) for t, l in self.lines if t_start is None or (t_start <= t <= t_end + 0.03)]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to the whole run (warm-up + timed)
+            inside, window = self.lines, "warm-up + timed region"
+        sm, smax, reasons, power = parse(inside)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "window": window, "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -220,21 +231,23 @@ def run_ours(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     start, end = ev(), ev()
     barrier()
+    t_start = time.time()
     start.record()
     for _ in range(args.steps):
         step(record=True)
     end.record()
     barrier()
+    t_end = time.time()
     elapsed_ms = start.elapsed_time(end)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_start, t_end) if rank == 0 else None
     mlp_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in mlp_events)
 
     # ---- e2e: host buffers through the public API, copies inside the timed region ----
@@ -307,7 +320,7 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))

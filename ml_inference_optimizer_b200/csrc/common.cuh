@@ -213,10 +213,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
 // Instruction descriptor for kind::f16 (bf16 or fp16 inputs, fp32 accumulate).
 //   bits [4,6) c_format=1 (f32); [7,10) a_format; [10,13) b_format (0=f16, 1=bf16);
 //   bit 15 a_major, bit 16 b_major (0 = K-major, 1 = MN-major); [17,23) N>>3; [24,29) M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool is_bf16, bool a_mn_major, bool b_mn_major) {
-  return (1u << 4) | ((is_bf16 ? 1u : 0u) << 7) | ((is_bf16 ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
+__host__ __device__ constexpr uint32_t make_idesc_f16_ab(int m, int n, bool a_is_bf16, bool b_is_bf16, bool a_mn_major,
+                                                         bool b_mn_major) {
+  return (1u << 4) | ((a_is_bf16 ? 1u : 0u) << 7) | ((b_is_bf16 ? 1u : 0u) << 10) | ((a_mn_major ? 1u : 0u) << 15) |
          ((b_mn_major ? 1u : 0u) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool is_bf16, bool a_mn_major, bool b_mn_major) {
+  return make_idesc_f16_ab(m, n, is_bf16, is_bf16, a_mn_major, b_mn_major);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]

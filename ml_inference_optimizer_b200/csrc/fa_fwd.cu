@@ -38,25 +38,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, safe for bf16/fp16 P and fp32 sums
 
-// 2^x for a pair of values on the FMA pipe (no MUFU): Cody-Waite range reduction with the 1.5*2^23 rounding constant,
-// degree-3 minimax polynomial on [-0.5, 0.5] (max rel. error 7.5e-5, far below the 2^-9 rounding of the 16-bit P),
-// exponent re-inserted with an integer add. Half of the exponentials of a tile go this way so the 16-lane/clk
-// MUFU pipe is not the bound of the softmax (the same idea as FlashAttention-4's software exp2).
-__device__ __forceinline__ float2 poly_exp2_pair(float2 x) {
-  x.x = fmaxf(x.x, -126.f);
-  x.y = fmaxf(x.y, -126.f);
-  const float2 j = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));
-  const float2 n = __fadd2_rn(j, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
-  float2 pl = __ffma2_rn(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
-  pl = __ffma2_rn(pl, f, make_float2(0.6932609677f, 0.6932609677f));
-  pl = __ffma2_rn(pl, f, make_float2(0.9999280572f, 0.9999280572f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(pl.x) + (__float_as_int(j.x) << 23));
-  r.y = __int_as_float(__float_as_int(pl.y) + (__float_as_int(j.y) << 23));
-  return r;
-}
-
 template <int D>
 struct Cfg {
   static constexpr int TILE_BYTES = 128 * D * 2;            // one Q / K / V tile
@@ -377,10 +358,10 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const float2 nm2 = make_float2(-m_ref, -m_ref);
       float2 sum2 = make_float2(0.f, 0.f);
       uint32_t pk0[32], pk1[32];
-      // columns c, c+1; packed fp32x2 FMA / ADD halve the issue slots. `poly` pairs use the FMA-pipe exp2.
-      auto exp_pair = [&](int c, bool poly) -> uint32_t {
+      // columns c, c+1: packed fp32x2 FMA / ADD halve the issue slots of the scale-subtract and the row sum
+      auto exp_pair = [&](int c) -> uint32_t {
         const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
-        const float2 e = poly ? poly_exp2_pair(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
         sum2 = __fadd2_rn(sum2, e);
         return Pack2<T>::pack(e.x, e.y);
       };
@@ -389,31 +370,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_half[2 * t + half]);
       };
-      // warp-uniform choice: tcgen05.st / the barrier arrive below are warp-collective
-      if (!__any_sync(0xffffffffu, limit < BLOCK_N)) {
-        // unmasked tile (the common case): every other pair on the FMA pipe
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i, (i & 1) != 0);
-        tmem_st_x32(tP, pk0);
-        if (wg_tid == 0) FA_STAMP(t, j, 3);
+      for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+      tmem_st_x32(tP, pk0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i, (i & 1) != 0);
-        if (wg_tid == 0) FA_STAMP(t, j, 4);
-        publish(0);  // the first half of P has landed: its P V MMAs start while we finish the row
-        if (wg_tid == 0) FA_STAMP(t, j, 5);
+      for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i);
+      publish(0);  // the first half of P has landed by now: its P V MMAs start while we finish the row
 #pragma unroll
-        for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i, (i & 1) != 0);
-        tmem_st_x32(tP + 32, pk1);
-      } else {
-        // masked tile (diagonal / ragged tail): MUFU only, so exp2(-inf) is exactly 0
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i, false);
-        tmem_st_x32(tP, pk0);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i, false);
-        publish(0);
-        tmem_st_x32(tP + 32, pk1);
-      }
+      for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i);
+      tmem_st_x32(tP + 32, pk1);
       l_run += sum2.x + sum2.y;
       if (wg_tid == 0) FA_STAMP(t, j, 6);
       publish(1);

@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 t = buf.cpu().view(4, 64, 8)
 base = t[t > 0].min().item()
 names = {0: "softmax0", 1: "softmax1", 2: "mma(t=0)", 3: "mma(t=1)"}
-lab_s = ["s_ready", "ld_done", "max_done", "half0_done", "q3_done", "pub0_done", "q4+st", "pub1_done"]
+lab_s = ["s_ready", "ld_done", "max_done", "-", "-", "-", "exp+st", "published"]
 lab_m = ["wait_p", "p_ready", "pv_issued", "qk_issued"]
 for slot in range(4):
     print("==", names[slot], lab_s if slot < 2 else lab_m)
@@ -34,8 +34,8 @@ for slot in range(4):
 for slot in (0, 1):
     d = (t[slot, 9:40, 0] - t[slot, 8:39, 0]).float()
     print(names[slot], "period mean", d.mean().item(), "min", d.min().item(), "max", d.max().item())
-    for a in range(7):
-        print(f"   {lab_s[a]:10s} -> {lab_s[a + 1]:10s} {(t[slot, 8:40, a + 1] - t[slot, 8:40, a]).float().mean().item():8.1f}")
+    for a, b in ((0, 1), (1, 2), (2, 6), (6, 7)):
+        print(f"   {lab_s[a]:10s} -> {lab_s[b]:10s} {(t[slot, 8:40, b] - t[slot, 8:40, a]).float().mean().item():8.1f}")
     print(f"   pub1_done -> next s_ready {(t[slot, 9:40, 0] - t[slot, 8:39, 7]).float().mean().item():8.1f}")
 for slot in (2, 3):
     for a, b, name in ((0, 1, "wait P"), (1, 2, "issue PV"), (2, 3, "issue QK")):
