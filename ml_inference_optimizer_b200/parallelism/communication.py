@@ -26,6 +26,14 @@ def initialize_distributed(local_rank: int, world_size: int, backend: str = "ncc
     if backend == "nccl":
         torch.cuda.set_device(local_rank)
         kwargs["device_id"] = torch.device("cuda", local_rank)
+        # NCCL kernels must get SMs while an attention / GEMM kernel still has CTAs queued, otherwise the ring hop is
+        # not overlapped but appended: run them on a high-priority stream
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            kwargs["pg_options"] = opts
+        except Exception:  # noqa: BLE001
+            pass
     dist.init_process_group(backend=backend, world_size=world_size, rank=int(os.environ.get("RANK", local_rank)), **kwargs)
 
 
@@ -198,7 +206,7 @@ class RingExchange:
         cuda = send[0].is_cuda
         if cuda and self.use_side_stream:
             if self.stream is None:
-                self.stream = torch.cuda.Stream(device=send[0].device)
+                self.stream = torch.cuda.Stream(device=send[0].device, priority=-1)
             self.stream.wait_stream(torch.cuda.current_stream(send[0].device))
             ctx = torch.cuda.stream(self.stream)
         else:

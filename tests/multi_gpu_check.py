@@ -18,7 +18,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+    dist.init_process_group("nccl", device_id=dev, pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
     from oracle import attn_mlp_oracle as orc
     from parallelism import communication as comm
     from parallelism import parallel_utils as pu
