@@ -21,7 +21,6 @@ namespace decode {
 
 constexpr int NUM_WARPS = 8;
 constexpr int NUM_THREADS = NUM_WARPS * 32;
-constexpr int NLOAD = 8;  // 16-byte loads in flight per lane for K (and again for V)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -51,8 +50,10 @@ struct Params {
 };
 
 template <int D, int G, typename T, bool PAGED>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 decode_kernel(const Params p) {
+  // 16-byte loads in flight per lane for K (and again for V); fewer for wide GQA groups so that two CTAs fit per SM
+  constexpr int NLOAD = (G >= 4) ? 4 : 8;
   constexpr int LPR = D / 8;          // lanes per KV row
   constexpr int RPW = 32 / LPR;       // rows per warp-wide load
   constexpr int TILE = NLOAD * RPW;   // keys per warp iteration
