@@ -219,12 +219,11 @@ def run_ours(args, w):
     def step(record=False):
         ops.flash_attn_fwd(q, k, v, causal=True, out=o)
         if record:
-            a, b_ = ev(), ev()
-            a.record()
-        ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg, out=y)
-        if record:
-            b_.record()
-            mlp_events.append((a, b_))
+            evs = (ev(), ev(), ev())
+            ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg, out=y, timing_events=evs)
+            mlp_events.append(evs)
+        else:
+            ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg, out=y)
 
     def barrier():
         if world > 1:
@@ -248,7 +247,9 @@ def run_ours(args, w):
     t_end = time.time()
     elapsed_ms = start.elapsed_time(end)
     clocks = sampler.stop(t_start, t_end) if rank == 0 else None
-    mlp_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in mlp_events)
+    gemm1_ms = statistics.mean(a.elapsed_time(b_) for a, b_, _ in mlp_events)
+    gemm2_ms = statistics.mean(b_.elapsed_time(c_) for _, b_, c_ in mlp_events)
+    attn_ms = elapsed_ms / args.steps - gemm1_ms - gemm2_ms
 
     # ---- e2e: host buffers through the public API, copies inside the timed region ----
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
@@ -291,7 +292,8 @@ def run_ours(args, w):
     if rank == 0:
         peaks = measured_peaks()
         peak = peaks["tflops_sustained"]  # the kernel is timed inside a long step
-        achieved = fm / (mlp_ms * 1e-3) / 1e12
+        gemm1_flops = (4.0 if act == "swiglu" else 2.0) * T * h * i   # up (+ gate) projection of the FusedMLP
+        achieved = gemm1_flops / (gemm1_ms * 1e-3) / 1e12
         cpu = cpu_oracle_rate(w, steps=2, warmup=1) if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": "fwd attention + FusedMLP TFLOP/s (causal attn + MLP layer step)", "value": value, "unit": "TFLOP/s",
@@ -300,10 +302,14 @@ def run_ours(args, w):
             "config": {"workload": w["name"], "parallelism": f"dp{world} (independent batches per GPU, no collective)",
                        "l2": "inputs (q,k,v,x = %.0f MB per step) exceed the 126 MB L2" % (h2d / 1e6),
                        "attn_flops_per_step": fa, "mlp_flops_per_step": fm},
-            "roofline": {"kernel": "gemm_act_kernel (FusedMLP: SwiGLU/GELU up+gate GEMM and down GEMM, 2 launches)",
+            "roofline": {"kernel": "gemm_act_kernel<%s> (FusedMLP up%s GEMM with the activation fused in the epilogue)" %
+                                   (act, "+gate" if act == "swiglu" else ""),
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                         "ms_per_launch_pair": mlp_ms, "traffic": None},
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}): kernel timed inside a long step",
+                         "ms_per_launch": gemm1_ms, "flops_per_launch": gemm1_flops,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_gemm1_v0_ncu.txt)
+                         "traffic": 3.872766e9 if args.workload == "c3" else None,
+                         "other_kernels_ms": {"fa_fwd_kernel": attn_ms, "gemm_act_kernel<none> (down projection)": gemm2_ms}},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": 3 * args.steps,

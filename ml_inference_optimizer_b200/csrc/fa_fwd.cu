@@ -47,9 +47,18 @@ struct Cfg {
   static constexpr int SMEM_KV_OFF = 2 * TILE_BYTES;
   static constexpr int SMEM_BAR_OFF = SMEM_KV_OFF + KV_STAGES * TILE_BYTES;
   static constexpr int SMEM_BYTES = SMEM_BAR_OFF + 512 + 1024;
-  static constexpr uint32_t TMEM_S = 0;      // + t * 128
-  static constexpr uint32_t TMEM_P_OFF = 64; // inside the S region
-  static constexpr uint32_t TMEM_O = 256;    // + t * D
+  // D = 128 fills TMEM: [S0 | S1 | O0 | O1], P_t overlays the upper half of S_t, so Q_t K(j+1)^T has to wait for P_t(j) V(j).
+  // D = 64 leaves room for separate P buffers: [S0 | S1 | P0 | P1 | O0 | O1]; S_t is free as soon as the softmax warps
+  // have read it, so the next Q K^T can be issued during the exponentials ("decoupled" pipeline, -DB200_FA_DECOUPLE).
+#ifdef B200_FA_DECOUPLE
+  static constexpr bool DECOUPLED = (D == 64);
+#else
+  static constexpr bool DECOUPLED = false;  // measured: both tiles then run in lockstep and share the MUFU pipe (606 vs 701 TFLOP/s)
+#endif
+  static constexpr uint32_t TMEM_S = 0;                          // + t * 128
+  static constexpr uint32_t TMEM_P = DECOUPLED ? 256 : 64;       // + t * (DECOUPLED ? 64 : 128)
+  static constexpr uint32_t TMEM_P_STRIDE = DECOUPLED ? 64 : 128;
+  static constexpr uint32_t TMEM_O = DECOUPLED ? 384 : 256;      // + t * D
 };
 
 struct Params {
@@ -91,7 +100,8 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* s_full = kv_empty + NS;                                        // [2]  MMA -> softmax
   uint64_t* p_half = s_full + 2;                                           // [2][2] softmax -> MMA: P columns [0,64) / [64,128) stored (one arrival per warp)
   uint64_t* pv_done = p_half + 4;                                          // [2]  MMA -> softmax (O_t updated)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_free = pv_done + 2;                                          // [2]  softmax -> MMA: S_t has been read (decoupled pipeline)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -121,6 +131,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(&p_half[2 * i], 4);
       mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -204,7 +215,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       auto issue_pv = [&](int t, int v_stage, int part, bool accumulate) {
         const uint64_t vd = vdesc0 + static_cast<uint64_t>(v_stage * TILE16);
         const uint32_t d_tmem = tmem_base + C::TMEM_O + static_cast<uint32_t>(t * D);
-        const uint32_t p_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128) + C::TMEM_P_OFF;
+        const uint32_t p_tmem = tmem_base + C::TMEM_P + static_cast<uint32_t>(t) * C::TMEM_P_STRIDE;
         if (elect_one()) {
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -239,37 +250,68 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         k_stage = v_stage + 1;
         k_phase = v_phase;
         if (k_stage == NS) { k_stage = 0; k_phase ^= 1; }
-        mbar_wait(&kv_full[v_stage], v_phase);
         const bool has_next = (j + 1 < n_max);
-        bool next_k_ready = false;
+        if constexpr (C::DECOUPLED) {
+          // next Q K^T first: it only needs K(j+1) and the softmax warps to have READ S_t(j)
+          if (has_next) {
+            mbar_wait(&kv_full[k_stage], k_phase);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int nt_t = t == 0 ? n0 : n1;
-          if (j < nt_t) {
-            if (lane == 0) FA_STAMP(2 + t, j, 0);
-            mbar_wait(&p_half[2 * t], static_cast<uint32_t>(j & 1));
-            tc_fence_after();
-            if (lane == 0) FA_STAMP(2 + t, j, 1);
-            issue_pv(t, v_stage, 0, j > 0);
-            mbar_wait(&p_half[2 * t + 1], static_cast<uint32_t>(j & 1));
-            tc_fence_after();
-            issue_pv(t, v_stage, 1, true);
-            if (lane == 0) FA_STAMP(2 + t, j, 2);
-          }
-          if (j + 1 < nt_t) {
-            if (!next_k_ready) {
-              mbar_wait(&kv_full[k_stage], k_phase);
-              tc_fence_after();
-              next_k_ready = true;
+            for (int t = 0; t < 2; ++t) {
+              const int nt_t = t == 0 ? n0 : n1;
+              if (j + 1 < nt_t) {
+                mbar_wait(&s_free[t], static_cast<uint32_t>(j & 1));
+                tc_fence_after();
+                issue_qk(t, k_stage);
+              }
             }
-            issue_qk(t, k_stage);
-            if (lane == 0) FA_STAMP(2 + t, j, 3);
+            release(k_stage);
           }
-        }
-        release(v_stage);
-        if (has_next) {
-          if (!next_k_ready) mbar_wait(&kv_full[k_stage], k_phase);
-          release(k_stage);
+          mbar_wait(&kv_full[v_stage], v_phase);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int nt_t = t == 0 ? n0 : n1;
+            if (j < nt_t) {
+              mbar_wait(&p_half[2 * t], static_cast<uint32_t>(j & 1));
+              tc_fence_after();
+              issue_pv(t, v_stage, 0, j > 0);
+              mbar_wait(&p_half[2 * t + 1], static_cast<uint32_t>(j & 1));
+              tc_fence_after();
+              issue_pv(t, v_stage, 1, true);
+            }
+          }
+          release(v_stage);
+        } else {
+          mbar_wait(&kv_full[v_stage], v_phase);
+          bool next_k_ready = false;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int nt_t = t == 0 ? n0 : n1;
+            if (j < nt_t) {
+              if (lane == 0) FA_STAMP(2 + t, j, 0);
+              mbar_wait(&p_half[2 * t], static_cast<uint32_t>(j & 1));
+              tc_fence_after();
+              if (lane == 0) FA_STAMP(2 + t, j, 1);
+              issue_pv(t, v_stage, 0, j > 0);
+              mbar_wait(&p_half[2 * t + 1], static_cast<uint32_t>(j & 1));
+              tc_fence_after();
+              issue_pv(t, v_stage, 1, true);
+              if (lane == 0) FA_STAMP(2 + t, j, 2);
+            }
+            if (j + 1 < nt_t) {
+              if (!next_k_ready) {
+                mbar_wait(&kv_full[k_stage], k_phase);
+                tc_fence_after();
+                next_k_ready = true;
+              }
+              issue_qk(t, k_stage);
+              if (lane == 0) FA_STAMP(2 + t, j, 3);
+            }
+          }
+          release(v_stage);
+          if (has_next) {
+            if (!next_k_ready) mbar_wait(&kv_full[k_stage], k_phase);
+            release(k_stage);
+          }
         }
       }
     }
@@ -285,7 +327,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const int nt = t == 0 ? n0 : n1;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + C::TMEM_S + static_cast<uint32_t>(t * 128);
-    const uint32_t tP = tS + C::TMEM_P_OFF;
+    const uint32_t tP = tmem_base + lane_addr + C::TMEM_P + static_cast<uint32_t>(t) * C::TMEM_P_STRIDE;
     const uint32_t tO = tmem_base + lane_addr + C::TMEM_O + static_cast<uint32_t>(t * D);
     uint8_t* sO = smem + C::SMEM_Q_OFF + t * C::TILE_BYTES;  // Q_t's smem is reused for the output tile
 
@@ -303,6 +345,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tmem_ld_x32(tS + 64, s + 64);
       tmem_ld_x32(tS + 96, s + 96);
       tmem_wait_ld();
+      if constexpr (C::DECOUPLED) {
+        // S_t is in registers: the MMA warp may overwrite it with Q_t K(j+1)^T while we do the softmax
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+      }
       if (wg_tid == 0) FA_STAMP(t, j, 1);
       // ---- masking: keys >= limit (relative to the tile) are invisible ----
       const int kv0 = j * BLOCK_N;
@@ -338,7 +386,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         l_run *= alpha;
         rescale = true;
       }
-      if (__any_sync(0xffffffffu, rescale)) {
+      const bool any_rescale = __any_sync(0xffffffffu, rescale);
+      if (C::DECOUPLED && j > 0 && !any_rescale) {
+        // the separate P_t buffer may only be rewritten once P_t(j-1) V(j-1) has consumed it
+        mbar_wait(&pv_done[t], static_cast<uint32_t>((j - 1) & 1));
+      }
+      if (any_rescale) {
         // O_t must contain P(j-1) V(j-1) before it is rescaled
         mbar_wait(&pv_done[t], static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
