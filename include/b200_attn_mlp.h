@@ -57,6 +57,11 @@ const char* b200_last_error(void);
 /* 1 if the current CUDA device is compute capability 10.x, 0 if not, negative error if no device. */
 int b200_arch_ok(void);
 
+/* Process-wide cap on the CTAs of the persistent GEMM kernels (0 = all SMs). The tensor-parallel MLP lowers it while an
+ * NCCL all-reduce of the previous token chunk is in flight so that the collective finds free SMs (overlap instead of
+ * serialisation, parallelism/tensor_parallel.py:302 rebuilt). */
+int b200_set_sm_limit(int max_ctas);
+
 /* ---- K1: tiled online-softmax attention forward (prefill) -------------------------------------------
  * Replaces triton_flash_attention / _flash_attention_forward_kernel
  *   (kernels/triton/flash_attention_kernels.py:1150-1358, :38-325), the attention inside
@@ -131,8 +136,8 @@ int b200_kv_append(const void* key, const void* value, void* k_cache, void* v_ca
  *      y = (silu(x W_gate^T + b_gate) * (x W_up^T + b_up)) W_down^T + b_down          (SWIGLU)
  *   x [T, h] (row stride ldx), w_up / w_gate [i, h], w_down [h_out, i] in nn.Linear layout ([out, in], row
  *   contiguous), biases [i] / [h_out] or NULL, y [T, h_out] (row stride ldy). h, i, h_out multiples of 8.
- *   workspace: T * i elements of `dtype` for the activated intermediate (it is written once and consumed
- *   from L2 by the down projection).                                                      */
+ *   workspace: b200_fused_mlp_workspace_bytes(T, h, i) bytes: the activated 16-bit intermediate [T, i] (written once,
+ *   consumed by the down projection) plus split-K partials for decode-sized T; see DESIGN.md.           */
 int64_t b200_fused_mlp_workspace_bytes(int64_t T, int h, int i);
 int b200_fused_mlp(const void* x, int64_t ldx, const void* w_up, const void* b_up, const void* w_gate,
                    const void* b_gate, const void* w_down, const void* b_down, void* y, int64_t ldy, int64_t T,
@@ -142,9 +147,12 @@ int b200_fused_mlp(const void* x, int64_t ldx, const void* w_up, const void* b_u
 /* One tcgen05 GEMM with a fused epilogue: y = act(x W^T + b) (or the SwiGLU pair form when w_gate != NULL).
  * This is ColumnParallelLinear/RowParallelLinear's F.linear (parallelism/tensor_parallel.py:173, :299) and
  * the building block of b200_fused_mlp. x [T,K] (ldx), w [N,K], y [T,N] (ldy).                          */
+/* workspace: optional device scratch of b200_linear_act_workspace_bytes(...) bytes; when present, skinny problems
+ * (few output tiles, long K: decode-sized T) run split-K across the SMs with an fp32 reduce pass. NULL = never split. */
+int64_t b200_linear_act_workspace_bytes(int64_t T, int K, int N, int act);
 int b200_linear_act(const void* x, int64_t ldx, const void* w, const void* b, const void* w_gate,
-                    const void* b_gate, void* y, int64_t ldy, int64_t T, int K, int N, int act, int dtype,
-                    void* stream);
+                    const void* b_gate, void* y, int64_t ldy, int64_t T, int K, int N, int act, void* workspace,
+                    int64_t workspace_bytes, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ SIGNATURES = {
     "b200_version": (c_char_p, []),
     "b200_last_error": (c_char_p, []),
     "b200_arch_ok": (c_int, []),
+    "b200_set_sm_limit": (c_int, [c_int]),
     "b200_fa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_float, c_int, c_int64, c_void_p, c_int,
                             c_void_p]),
@@ -39,8 +40,9 @@ SIGNATURES = {
     "b200_fused_mlp_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "b200_fused_mlp": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "b200_linear_act_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "b200_linear_act": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                c_int, c_int, c_int, c_int, c_void_p]),
+                                c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
 }
 
 

@@ -43,9 +43,19 @@ struct Params {
   const void* bias0;     // [N_out] bias (SwiGLU: gate bias) or nullptr
   const void* bias1;     // SwiGLU: up bias or nullptr
   int num_m_blocks, num_n_blocks, num_k_blocks, num_tiles;
+  // split-K (skinny problems: few output tiles, long K): tile index = mn_tile * k_splits + split; each split accumulates
+  // k-blocks [split*kb_per_split, ...) and stores raw fp32 accumulators to `partial` [k_splits][M][num_n_blocks*256]
+  int k_splits, kb_per_split;
+  float* partial;
+  void* y;       // output pointer / row stride for the split-K reduce pass
+  int64_t ldy;
 };
 
-__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(const Params& p, int tile_in, int& m_blk, int& n_blk, int& kb0, int& kb1) {
+  const int split = tile_in % p.k_splits;
+  const int tile = tile_in / p.k_splits;
+  kb0 = split * p.kb_per_split;
+  kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
   const int per_group = GROUP_M * p.num_n_blocks;
   const int group = tile / per_group;
   const int first_m = group * GROUP_M;
@@ -145,11 +155,11 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(p, tile, m_blk, n_blk);
+        int m_blk, n_blk, kb0, kb1;
+        tile_coords(p, tile, m_blk, n_blk, kb0, kb1);
         const int m0 = m_blk * BM;
         const int n0 = n_blk * OUT_COLS;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
           uint8_t* sa = smem + SMEM_A_OFF + stage * A_STAGE_BYTES;
@@ -177,10 +187,12 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int m_blk_, n_blk_, kb0, kb1;
+      tile_coords(p, tile, m_blk_, n_blk_, kb0, kb1);
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * (A_STAGE_BYTES >> 4));
@@ -189,7 +201,7 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             umma_ss(d_tmem, ad + static_cast<uint64_t>(k * 2), bd + static_cast<uint64_t>(k * 2), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+                    (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
         }
@@ -210,13 +222,35 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t acc_phase = 0;
     int cbuf = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      int m_blk, n_blk;
-      tile_coords(p, tile, m_blk, n_blk);
+      int m_blk, n_blk, kb0, kb1;
+      tile_coords(p, tile, m_blk, n_blk, kb0, kb1);
       const int m0 = m_blk * BM;
       const int n0 = n_blk * OUT_COLS;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>(acc * BN);
+
+      if (p.k_splits > 1) {
+        // split-K: raw fp32 accumulators of this split -> workspace; bias / activation happen in splitk_reduce_kernel
+        const int split = tile % p.k_splits;
+        const int64_t ld = static_cast<int64_t>(p.num_n_blocks) * BN;
+        float* dst = p.partial + (static_cast<int64_t>(split) * p.M + (m0 + row)) * ld + static_cast<int64_t>(n_blk) * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_x32(t_acc + c * 32, v);
+          tmem_wait_ld();
+          if (m0 + row < p.M) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(dst + c * 32 + q * 4) = make_uint4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
 
 #pragma unroll 1
       for (int chunk = 0; chunk < OUT_COLS / 64; ++chunk) {
@@ -289,6 +323,55 @@ gemm_act_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
+// split-K second pass: sum the per-split fp32 partials, add bias, apply the activation (SwiGLU pairs gate/up columns
+// of the same tile), convert to 16 bit. One thread per 8 output columns.
+template <int ACT, typename T>
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int k_splits, int M, int N_out, int num_n_blocks,
+                                     const void* __restrict__ bias0, const void* __restrict__ bias1, T* __restrict__ y,
+                                     int64_t ldy) {
+  constexpr bool kSwiglu = (ACT == B200_ACT_SWIGLU);
+  constexpr int OUT_COLS = kSwiglu ? 128 : 256;
+  const int vec_per_row = (N_out + 7) / 8;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(M) * vec_per_row) return;
+  const int m = static_cast<int>(idx / vec_per_row);
+  const int n = static_cast<int>(idx % vec_per_row) * 8;
+  const int nb = n / OUT_COLS, c = n % OUT_COLS;
+  const int64_t ld = static_cast<int64_t>(num_n_blocks) * BN;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < k_splits; ++s) {
+    const float* src = partial + (static_cast<int64_t>(s) * M + m) * ld + static_cast<int64_t>(nb) * BN + c;
+    const float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+    a[0] += v0.x; a[1] += v0.y; a[2] += v0.z; a[3] += v0.w; a[4] += v1.x; a[5] += v1.y; a[6] += v1.z; a[7] += v1.w;
+    if constexpr (kSwiglu) {
+      const float4 w0 = *reinterpret_cast<const float4*>(src + 128), w1 = *reinterpret_cast<const float4*>(src + 132);
+      u[0] += w0.x; u[1] += w0.y; u[2] += w0.z; u[3] += w0.w; u[4] += w1.x; u[5] += w1.y; u[6] += w1.z; u[7] += w1.w;
+    }
+  }
+  float b0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto load_bias = [&](const void* bias, float* out) {
+    if (bias == nullptr) return;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(bias) + n));
+    float2 f;
+    f = Pack2<T>::unpack(v.x); out[0] = f.x; out[1] = f.y;
+    f = Pack2<T>::unpack(v.y); out[2] = f.x; out[3] = f.y;
+    f = Pack2<T>::unpack(v.z); out[4] = f.x; out[5] = f.y;
+    f = Pack2<T>::unpack(v.w); out[6] = f.x; out[7] = f.y;
+  };
+  load_bias(bias0, b0);
+  if constexpr (kSwiglu) load_bias(bias1, b1);
+  float r[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if constexpr (kSwiglu) r[e] = silu(a[e] + b0[e]) * (u[e] + b1[e]);
+    else r[e] = apply_act<ACT>(a[e] + b0[e]);
+  }
+  uint4 pk;
+  pk.x = Pack2<T>::pack(r[0], r[1]); pk.y = Pack2<T>::pack(r[2], r[3]);
+  pk.z = Pack2<T>::pack(r[4], r[5]); pk.w = Pack2<T>::pack(r[6], r[7]);
+  *reinterpret_cast<uint4*>(y + static_cast<int64_t>(m) * ldy + n) = pk;
+}
+
 template <int ACT, typename T>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap& tb1, const CUtensorMap& tc,
            const Params& p, cudaStream_t stream) {
@@ -298,9 +381,17 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap& tb1
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  int max_ctas = sm_count();
+  if (sm_limit() > 0 && sm_limit() < max_ctas) max_ctas = sm_limit();  // leave SMs to a concurrent collective
+  const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb0, tb1, tc, p);
   B200_CUDA_OK(cudaGetLastError());
+  if (p.k_splits > 1) {
+    const int64_t total = static_cast<int64_t>(p.M) * ((p.N_out + 7) / 8);
+    splitk_reduce_kernel<ACT, T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        p.partial, p.k_splits, p.M, p.N_out, p.num_n_blocks, p.bias0, p.bias1, static_cast<T*>(p.y), p.ldy);
+    B200_CUDA_OK(cudaGetLastError());
+  }
   return B200_OK;
 }
 
@@ -327,8 +418,30 @@ static int check_ptr16(const void* p, const char* name) {
 }
 
 // y[T,N] = act(x[T,K] w[N,K]^T + b)      or      y = silu(x wg^T + bg) * (x w^T + b)  when act == SWIGLU
+// number of K splits for a problem with `tiles` output tiles and `kblocks` 64-wide K blocks: only skinny problems
+// (fewer output tiles than SMs) are split, into enough pieces to fill the machine, keeping >= 4 k-blocks per split
+static int choose_k_splits(int tiles, int kblocks) {
+  const int sms = sm_count();
+  if (tiles >= sms || kblocks < 8) return 1;
+  int splits = sms / tiles;  // one wave: every CTA resident at once, the fp32 reduce pass stays small
+  if (splits > kblocks / 4) splits = kblocks / 4;
+  if (splits > 32) splits = 32;
+  return splits < 1 ? 1 : splits;
+}
+
+int64_t linear_act_workspace_bytes(int64_t T, int K, int N, int act) {
+  if (T <= 0 || K <= 0 || N <= 0) return 0;
+  const int out_cols = (act == B200_ACT_SWIGLU) ? 128 : 256;
+  const int64_t m_blocks = (T + gemm::BM - 1) / gemm::BM, n_blocks = (N + out_cols - 1) / out_cols;
+  if (m_blocks * n_blocks > 0x7fffffff) return 0;
+  const int splits = choose_k_splits(static_cast<int>(m_blocks * n_blocks), (K + gemm::BK - 1) / gemm::BK);
+  if (splits <= 1) return 0;
+  return static_cast<int64_t>(splits) * T * n_blocks * gemm::BN * static_cast<int64_t>(sizeof(float));
+}
+
 int linear_act_impl(const void* x, int64_t ldx, const void* w, const void* b, const void* w_gate, const void* b_gate,
-                    void* y, int64_t ldy, int64_t T, int K, int N, int act, int dtype, cudaStream_t stream) {
+                    void* y, int64_t ldy, int64_t T, int K, int N, int act, int dtype, void* workspace,
+                    int64_t workspace_bytes, cudaStream_t stream) {
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "dtype must be bf16 or fp16");
   B200_CHECK_ARG(T >= 0 && K > 0 && N > 0, "bad sizes T=%lld K=%d N=%d", (long long)T, K, N);
   B200_CHECK_ARG(T <= 0x7fffffffLL, "T too large");
@@ -379,7 +492,19 @@ int linear_act_impl(const void* x, int64_t ldx, const void* w, const void* b, co
   p.num_m_blocks = (p.M + gemm::BM - 1) / gemm::BM;
   p.num_n_blocks = (N + out_cols - 1) / out_cols;
   p.num_k_blocks = (K + gemm::BK - 1) / gemm::BK;
-  p.num_tiles = p.num_m_blocks * p.num_n_blocks;
+  p.k_splits = 1;
+  p.partial = nullptr;
+  p.y = y;
+  p.ldy = ldy;
+  const int64_t ws_need = linear_act_workspace_bytes(T, K, N, act);
+  if (ws_need > 0 && workspace != nullptr && workspace_bytes >= ws_need &&
+      (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+    p.k_splits = choose_k_splits(p.num_m_blocks * p.num_n_blocks, p.num_k_blocks);
+    p.partial = static_cast<float*>(workspace);
+  }
+  p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
+  p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.num_tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
   if (dtype == B200_DTYPE_BF16) return gemm::dispatch<__nv_bfloat16>(act, ta, tb0, tb1, tc, p, stream);
   return gemm::dispatch<__half>(act, ta, tb0, tb1, tc, p, stream);
 }
@@ -388,16 +513,29 @@ int linear_act_impl(const void* x, int64_t ldx, const void* w, const void* b, co
 
 extern "C" {
 
+int64_t b200_linear_act_workspace_bytes(int64_t T, int K, int N, int act) {
+  return b200::linear_act_workspace_bytes(T, K, N, act);
+}
+
 int b200_linear_act(const void* x, int64_t ldx, const void* w, const void* b, const void* w_gate, const void* b_gate,
-                    void* y, int64_t ldy, int64_t T, int K, int N, int act, int dtype, void* stream) {
-  return b200::linear_act_impl(x, ldx, w, b, w_gate, b_gate, y, ldy, T, K, N, act, dtype,
+                    void* y, int64_t ldy, int64_t T, int K, int N, int act, void* workspace, int64_t workspace_bytes,
+                    int dtype, void* stream) {
+  return b200::linear_act_impl(x, ldx, w, b, w_gate, b_gate, y, ldy, T, K, N, act, dtype, workspace, workspace_bytes,
                                static_cast<cudaStream_t>(stream));
 }
 
+static int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
 int64_t b200_fused_mlp_workspace_bytes(int64_t T, int h, int i) {
-  (void)h;
   if (T < 0 || i <= 0) return 0;
-  return T * static_cast<int64_t>(i) * 2;
+  // intermediate [T, i] (16 bit) + split-K partials of the skinnier of the two GEMMs (worst case over activations)
+  const int64_t inter = align256(T * static_cast<int64_t>(i) * 2);
+  int64_t sk = b200::linear_act_workspace_bytes(T, h, i, B200_ACT_SWIGLU);
+  const int64_t sk1 = b200::linear_act_workspace_bytes(T, h, i, B200_ACT_NONE);
+  const int64_t sk2 = b200::linear_act_workspace_bytes(T, i, h, B200_ACT_NONE);
+  if (sk1 > sk) sk = sk1;
+  if (sk2 > sk) sk = sk2;
+  return inter + sk;
 }
 
 int b200_fused_mlp(const void* x, int64_t ldx, const void* w_up, const void* b_up, const void* w_gate,
@@ -411,10 +549,14 @@ int b200_fused_mlp(const void* x, int64_t ldx, const void* w_up, const void* b_u
                      (long long)b200_fused_mlp_workspace_bytes(T, h, i), (long long)workspace_bytes);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // GEMM1 + bias + activation (SwiGLU: gate/up pair) -> bf16 intermediate (stays L2-resident per row panel)
-  int rc = linear_act_impl(x, ldx, w_up, b_up, w_gate, b_gate, workspace, i, T, h, i, act, dtype, s);
+  const int64_t inter = align256(T * static_cast<int64_t>(i) * 2);
+  void* sk_ws = static_cast<char*>(workspace) + inter;
+  const int64_t sk_bytes = workspace_bytes - inter;
+  int rc = linear_act_impl(x, ldx, w_up, b_up, w_gate, b_gate, workspace, i, T, h, i, act, dtype, sk_ws, sk_bytes, s);
   if (rc) return rc;
   // GEMM2 + bias
-  return linear_act_impl(workspace, i, w_down, b_down, nullptr, nullptr, y, ldy, T, i, h_out, B200_ACT_NONE, dtype, s);
+  return linear_act_impl(workspace, i, w_down, b_down, nullptr, nullptr, y, ldy, T, i, h_out, B200_ACT_NONE, dtype, sk_ws,
+                         sk_bytes, s);
 }
 
 }  // extern "C"

@@ -3,6 +3,8 @@
 
 #include <cudaTypedefs.h>
 
+#include <atomic>
+
 namespace b200 {
 
 std::string& last_error_ref() {
@@ -67,6 +69,10 @@ int encode_tmap_sw128_16b(CUtensorMap* out, const void* base, int rank, const ui
   return B200_OK;
 }
 
+std::atomic<int> g_sm_limit{0};
+
+int sm_limit() { return g_sm_limit.load(std::memory_order_relaxed); }
+
 int sm_count() {
   static int cached[64];
   int dev = 0;
@@ -86,6 +92,12 @@ extern "C" {
 const char* b200_version(void) { return "b200_attn_mlp 0.1.0 (sm_100a)"; }
 
 const char* b200_last_error(void) { return b200::last_error_ref().c_str(); }
+
+int b200_set_sm_limit(int max_ctas) {
+  if (max_ctas < 0) return b200::set_error(B200_ERR_INVALID_ARGUMENT, "sm limit must be >= 0");
+  b200::g_sm_limit.store(max_ctas, std::memory_order_relaxed);
+  return B200_OK;
+}
 
 int b200_arch_ok(void) {
   int dev = 0;

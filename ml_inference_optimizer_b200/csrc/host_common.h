@@ -42,5 +42,6 @@ int encode_tmap_sw128_16b(CUtensorMap* out, const void* base, int rank, const ui
                           const uint32_t* box);
 
 int sm_count();  // multiprocessor count of the current device (cached per device)
+int sm_limit();  // b200_set_sm_limit value (0 = no limit): persistent kernels launch at most this many CTAs
 
 }  // namespace b200

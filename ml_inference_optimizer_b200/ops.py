@@ -289,9 +289,11 @@ def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     y = out.reshape(-1, N) if out is not None else torch.empty((T, N), dtype=x.dtype, device=dev)
     lib = _lib.load()
     with torch.cuda.device(dev):
+        ws_bytes = lib.b200_linear_act_workspace_bytes(T, K, N, act)
+        ws = _workspace(dev, ws_bytes)
         rc = lib.b200_linear_act(x2.data_ptr(), x2.stride(0) if T > 1 else K, weight.data_ptr(), _ptr(bias),
                                  _ptr(gate_weight), _ptr(gate_bias), y.data_ptr(), y.stride(0) if T > 1 else N, T, K, N,
-                                 act, dt, _stream_ptr(dev))
+                                 act, _ptr(ws), ws_bytes, dt, _stream_ptr(dev))
     check("b200_linear_act", rc)
     return y.reshape(*lead, N)
 
@@ -337,12 +339,15 @@ def fused_mlp(x: torch.Tensor, w_up: torch.Tensor, b_up: Optional[torch.Tensor],
             e0, e1, e2 = timing_events
             stream = torch.cuda.current_stream(dev)
             e0.record(stream)
+            inter = (T * i * 2 + 255) & ~255
+            sk_ptr, sk_bytes = ws.data_ptr() + inter, ws_bytes - inter
             rc = lib.b200_linear_act(x2.data_ptr(), x2.stride(0) if T > 1 else h, w_up.data_ptr(), _ptr(b_up), _ptr(w_gate),
-                                     _ptr(b_gate), ws.data_ptr(), i, T, h, i, act, dt, _stream_ptr(dev))
+                                     _ptr(b_gate), ws.data_ptr(), i, T, h, i, act, sk_ptr, sk_bytes, dt, _stream_ptr(dev))
             check("b200_linear_act", rc)
             e1.record(stream)
             rc = lib.b200_linear_act(ws.data_ptr(), i, w_down.data_ptr(), _ptr(b_down), None, None, y.data_ptr(),
-                                     y.stride(0) if T > 1 else h_out, T, i, h_out, ACT_NONE, dt, _stream_ptr(dev))
+                                     y.stride(0) if T > 1 else h_out, T, i, h_out, ACT_NONE, sk_ptr, sk_bytes, dt,
+                                     _stream_ptr(dev))
             check("b200_linear_act", rc)
             e2.record(stream)
             return y.reshape(*lead, h_out)
@@ -352,6 +357,15 @@ def fused_mlp(x: torch.Tensor, w_up: torch.Tensor, b_up: Optional[torch.Tensor],
                                 _stream_ptr(dev))
     check("b200_fused_mlp", rc)
     return y.reshape(*lead, h_out)
+
+
+def set_sm_limit(max_ctas: int) -> None:
+    """Cap the CTAs of the persistent GEMM kernels (0 = no cap); see ``b200_set_sm_limit``."""
+    check("b200_set_sm_limit", _lib.load().b200_set_sm_limit(int(max_ctas)))
+
+
+def sm_count(device=None) -> int:
+    return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
 
 
 def arch_ok() -> bool:

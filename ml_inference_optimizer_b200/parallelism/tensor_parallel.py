@@ -174,6 +174,10 @@ class TensorParallelMLP(nn.Module):
         self.activation = activation
         self.gated = gated
         self._local_mlp = None  # test hook: fn(x, w_up, b_up, w_down, act, w_gate, b_gate) -> partial output
+        # overlap of the all-reduce with the GEMMs of the next token chunk (prefill-sized inputs only)
+        self.overlap_chunks = 4
+        self.overlap_min_tokens = 8192
+        self.comm_sms = 16  # SMs left free for the collective while chunks are in flight
 
     @classmethod
     def from_dense(cls, w_up, b_up, w_down, b_down, config: TensorParallelConfig, activation: Callable = F.gelu,
@@ -195,11 +199,41 @@ class TensorParallelMLP(nn.Module):
             partial = self._local_mlp(hidden_states, up.weight, up.bias, down.weight, act, gw, gb)
         else:
             from .. import ops
+            lead = hidden_states.shape[:-1]
+            x2 = hidden_states.reshape(-1, hidden_states.shape[-1])
+            T = x2.shape[0]
+            if self.config.tp_size > 1 and self.overlap_chunks > 1 and T >= self.overlap_min_tokens and dist.is_initialized():
+                return self._forward_overlapped(x2, act, gw, gb).reshape(*lead, -1)
             # the down bias must be added once, after the reduction (reference :304-308)
             partial = ops.fused_mlp(hidden_states, up.weight, up.bias, down.weight, None, act, gw, gb)
         if self.config.tp_size > 1:
             comm.all_reduce(partial, group=self.config.get_tp_group())
         return partial if down.bias is None else partial + down.bias
+
+    def _forward_overlapped(self, x2: torch.Tensor, act: str, gw, gb) -> torch.Tensor:
+        """Token-chunked pipeline: while NCCL reduces chunk c (on its own high-priority stream, using the SMs the GEMMs
+        leave free), the GEMMs of chunk c+1 run. Same arithmetic as one fused call followed by one all-reduce."""
+        from .. import ops
+        up, down = self.dense_h_to_4h, self.dense_4h_to_h
+        T = x2.shape[0]
+        out = torch.empty(T, down.out_features, dtype=x2.dtype, device=x2.device)
+        group = self.config.get_tp_group()
+        n = self.overlap_chunks
+        rows = ((T + n - 1) // n + 127) // 128 * 128
+        works = []
+        ops.set_sm_limit(max(1, ops.sm_count(x2.device) - self.comm_sms))
+        try:
+            for r0 in range(0, T, rows):
+                r1 = min(T, r0 + rows)
+                ops.fused_mlp(x2[r0:r1], up.weight, up.bias, down.weight, None, act, gw, gb, out=out[r0:r1])
+                works.append(dist.all_reduce(out[r0:r1], group=group, async_op=True))
+        finally:
+            ops.set_sm_limit(0)
+        for w in works:
+            w.wait()
+        if down.bias is not None:
+            out += down.bias
+        return out
 
 
 class TensorParallelAttention(nn.Module):

@@ -59,6 +59,15 @@ def main():
         good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
         ok &= good
         print(f"[rank {rank}] tp mlp {name}: max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    # prefill-sized input: the chunked path that overlaps the all-reduce with the next chunk's GEMMs
+    xl = r(8192 + 77, h)
+    m = TensorParallelMLP.from_dense(c(wu), c(bu), c(wd), c(bd), cfg, F.silu, c(wg), c(bg))
+    y = m(c(xl))
+    ref = orc.mlp_ref(xl, wu, bu, wd, bd, "swiglu", wg, bg)
+    e = (y.float().cpu() - ref).abs().max().item()
+    good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
+    ok &= good
+    print(f"[rank {rank}] tp mlp swiglu overlapped (T={xl.shape[0]}): max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
     torch.manual_seed(5)  # same weights on every rank, then sharded
     H, Hk, Dh, hid = 8, 2 * world if world <= 4 else 8, 64, 512
     attn = TensorParallelAttention(hid, H, cfg, attention_dropout=0.0, num_kv_heads=Hk, causal=True)

@@ -38,3 +38,15 @@ elif what in ("decode", "decode_gqa"):
         ops.decode_attention(q, kc, vc, lens)
 torch.cuda.synchronize()
 print("done", what)
+if what == "mlp64":
+    T, h, i = 64, 4096, 11008
+    x = torch.randn(T, h, device="cuda", dtype=bf)
+    wu, wg = (torch.randn(i, h, device="cuda", dtype=bf) * 0.02 for _ in range(2))
+    wd = torch.randn(h, i, device="cuda", dtype=bf) * 0.02
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(reps):
+        flush.zero_()
+        ops.fused_mlp(x, wu, None, wd, None, "swiglu", wg, None)
+        flush.zero_()
+        torch.nn.functional.linear(torch.nn.functional.silu(torch.nn.functional.linear(x, wg)) * torch.nn.functional.linear(x, wu), wd)
+    torch.cuda.synchronize()

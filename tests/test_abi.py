@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_are_exported(built_lib):
     header = open(os.path.join(ROOT, "include", "b200_attn_mlp.h")).read()
     declared = sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header)))
-    assert len(declared) >= 13
+    assert len(declared) >= 14
     for name in declared:
         assert hasattr(built_lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
@@ -31,7 +31,8 @@ def test_header_cites_reference_interfaces():
 
 def test_version_and_pure_host_queries(built_lib):
     assert b"sm_100a" in built_lib.b200_version()
-    assert built_lib.b200_fused_mlp_workspace_bytes(32768, 4096, 11008) == 32768 * 11008 * 2
+    assert built_lib.b200_fused_mlp_workspace_bytes(32768, 4096, 11008) == 32768 * 11008 * 2  # wide problem: no split-K
+    assert built_lib.b200_linear_act_workspace_bytes(32768, 4096, 11008, 4) == 0
     assert built_lib.b200_fa_decode_workspace_bytes(4, 32, 8, 128, 8192, 1) == 0
     assert built_lib.b200_fa_decode_workspace_bytes(4, 32, 8, 128, 8192, 4) == 4 * 32 * 4 * 129 * 4
 
@@ -45,7 +46,7 @@ def test_invalid_arguments_return_error_codes(built_lib):
     assert rc == -1 and "multiple of Hkv" in _lib.last_error()
     rc = built_lib.b200_fa_fwd(dummy, dummy, dummy, dummy, None, 1, 128, 128, 2, 2, 96, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
     assert rc == -1 and "head_dim" in _lib.last_error()
-    rc = built_lib.b200_linear_act(dummy, 60, dummy, None, None, None, dummy, 64, 8, 60, 64, 0, 0, None)
+    rc = built_lib.b200_linear_act(dummy, 60, dummy, None, None, None, dummy, 64, 8, 60, 64, 0, None, 0, 0, None)
     assert rc == -1 and "multiples of 8" in _lib.last_error()
     rc = built_lib.b200_fused_mlp(dummy, 64, dummy, None, None, None, dummy, None, dummy, 64, 8, 64, 128, 64, 1, None, 0, 0, None)
     assert rc == -5 and "workspace" in _lib.last_error()

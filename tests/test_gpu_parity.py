@@ -260,6 +260,8 @@ MLP_CASES = [
     (300, 4096, 11008, "swiglu", False),     # Llama-2 layer shape, bias-less (HF Llama)
     (1, 768, 3072, "gelu_tanh", True),       # single token
     (130, 264, 520, "swiglu", True),         # nothing a multiple of the tile
+    (64, 4096, 11008, "swiglu", True),       # decode-sized T at Llama-2 widths: split-K path in both GEMMs
+    (8, 768, 3072, "gelu_tanh", True),       # decode-sized T at GPT-2 widths
 ]
 
 
@@ -313,9 +315,10 @@ def test_mlp_full_size_linearity(ops):
     y = ops.fused_mlp(x, wu, bu, wd, bd, "swiglu", wg, bg)
     rows = slice(20000, 20256)
     y_rows = ops.fused_mlp(x[rows].contiguous(), wu, bu, wd, bd, "swiglu", wg, bg)
-    assert torch.equal(y[rows], y_rows)
+    # the 256-row problem takes the split-K path (different fp32 summation order): equal up to bf16 rounding
+    assert (y[rows].float() - y_rows.float()).abs().max().item() <= 2e-2 * max(1.0, y_rows.float().abs().max().item() / 4)
     c = lambda t: t.cpu()
     ref = orc.mlp_ref(c(x[rows]), c(wu), c(bu), c(wd), c(bd), "swiglu", c(wg), c(bg))
     check_out(y_rows, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=1e-2)
     y0 = ops.fused_mlp(x[:512].contiguous(), wu, bu, torch.zeros_like(wd), bd, "swiglu", wg, bg)
-    assert torch.equal(y0, bd.view(1, -1).expand(512, -1))
+    assert torch.equal(y0, bd.view(1, -1).expand(512, -1))  # zero weights: exactly the bias on every path
