@@ -82,12 +82,21 @@ def main():
             pu.initialize_tensor_parallel(world)
         cfg = TensorParallelConfig(world_size=world, tp_size=world)
         mlp = TensorParallelMLP(h, i, cfg, F.silu, gated=True).to(dev, torch.bfloat16)
-        for T, tag in ((32768, "prefill"), (64, "decode")):
+        if os.environ.get("B200_TP_COMM_SMS"):
+            mlp.comm_sms = int(os.environ["B200_TP_COMM_SMS"])
+        if os.environ.get("B200_TP_CHUNKS"):
+            mlp.overlap_chunks = int(os.environ["B200_TP_CHUNKS"])
+        for T, tag in ((32768, "prefill"),) if args.quick else ((32768, "prefill"), (64, "decode")):
             x = torch.randn(T, h, device=dev, dtype=torch.bfloat16)
             ms = timed(lambda: mlp(x), args.warmup, args.iters, dev)
             flops = 6.0 * T * h * i
             emit({"bench": f"tp_mlp_swiglu_{tag}", "T": T, "hidden": h, "intermediate": i, "n_gpus": world, "ms": ms,
-                  "tflops_total": flops / ms / 1e9, "allreduce_bytes": T * h * 2})
+                  "tflops_total": flops / ms / 1e9, "allreduce_bytes": T * h * 2, "overlap_chunks": mlp.overlap_chunks,
+                  "comm_sms": mlp.comm_sms, "nccl_max_nchannels": os.environ.get("NCCL_MAX_NCHANNELS")})
+        if args.quick:
+            if world > 1:
+                dist.destroy_process_group()
+            return
         # head-parallel attention: Hq/tp query heads, Hkv/tp KV heads per rank (no collective inside attention)
         B, S = 4, 8192
         q = torch.randn(B, S, Hq // world, D, device=dev, dtype=torch.bfloat16)

@@ -56,7 +56,8 @@ def main():
         y = m(c(x))
         ref = orc.mlp_ref(x, wu, bu, wd, bd, "swiglu" if gate[0] is not None else "gelu", *gate)
         e = (y.float().cpu() - ref).abs().max().item()
-        good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
+        # partial sums are rounded to bf16 before the all-reduce: the error grows with the number of ranks
+        good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4) * (1 + world / 4)
         ok &= good
         print(f"[rank {rank}] tp mlp {name}: max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
     # prefill-sized input: the chunked path that overlaps the all-reduce with the next chunk's GEMMs
@@ -65,9 +66,14 @@ def main():
     y = m(c(xl))
     ref = orc.mlp_ref(xl, wu, bu, wd, bd, "swiglu", wg, bg)
     e = (y.float().cpu() - ref).abs().max().item()
-    good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4)
+    m.overlap_chunks = 1
+    y_plain = m(c(xl))  # one fused call + one all-reduce: the chunked pipeline must agree with it up to the reduction order
+    e2 = (y.float() - y_plain.float()).abs().max().item()
+    # partial sums are rounded to bf16 before the all-reduce (the reference reduces in the activation dtype too)
+    good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4) * (1 + world / 4) and e2 <= 2e-2
     ok &= good
-    print(f"[rank {rank}] tp mlp swiglu overlapped (T={xl.shape[0]}): max|dy|={e:.2e} {'OK' if good else 'FAIL'}", flush=True)
+    print(f"[rank {rank}] tp mlp swiglu overlapped (T={xl.shape[0]}): max|dy|={e:.2e} vs single all-reduce {e2:.2e} "
+          f"{'OK' if good else 'FAIL'}", flush=True)
     torch.manual_seed(5)  # same weights on every rank, then sharded
     H, Hk, Dh, hid = 8, 2 * world if world <= 4 else 8, 64, 512
     attn = TensorParallelAttention(hid, H, cfg, attention_dropout=0.0, num_kv_heads=Hk, causal=True)
