@@ -154,6 +154,16 @@ int b200_linear_act(const void* x, int64_t ldx, const void* w, const void* b, co
                     const void* b_gate, void* y, int64_t ldy, int64_t T, int K, int N, int act, void* workspace,
                     int64_t workspace_bytes, int dtype, void* stream);
 
+/* ---- LayerNorm (+ residual) — the op feeding the attention / MLP blocks --------------------
+ * Replaces triton_layernorm / _layernorm_fwd_kernel / _layernorm_residual_fwd_kernel
+ *   (kernels/triton/layernorm_kernels.py:191-277, :36-190):
+ *     y = LayerNorm(x + residual_alpha * residual) * weight + bias      (residual, bias may be NULL)
+ *   mean / biased variance over the last dimension in fp32 (two-pass), eps inside the sqrt (:305-308).
+ *   x, residual, y: [rows, cols] with row strides ldx/ldr/ldy (elements); cols % 8 == 0, cols <= 8192.            */
+int b200_layernorm(const void* x, const void* residual, const void* weight, const void* bias, void* y, int64_t rows,
+                   int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps, float residual_alpha, int dtype,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

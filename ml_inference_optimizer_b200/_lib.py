@@ -40,6 +40,8 @@ SIGNATURES = {
     "b200_fused_mlp_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "b200_fused_mlp": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "b200_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64,
+                               c_float, c_float, c_int, c_void_p]),
     "b200_linear_act_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "b200_linear_act": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                 c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),

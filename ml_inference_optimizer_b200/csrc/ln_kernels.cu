@@ -1,0 +1,226 @@
+// LayerNorm and LayerNorm(x + alpha * residual) for sm_100a — the op immediately before the attention / MLP blocks
+// (SURVEY.md §8 f3). Replaces _layernorm_fwd_kernel / _layernorm_residual_fwd_kernel / triton_layernorm
+// (kernels/triton/layernorm_kernels.py:36-190, :191-277).
+//
+// HBM-bound: each element is read once (x, and the residual when present) and written once. One CTA of 256 threads
+// per row; 128-bit loads, the row is held in fp32 registers between the mean pass and the variance pass (two-pass
+// variance like the reference's (x - u)^2 mean, not E[x^2] - u^2), block reduction by warp shuffles + shared memory.
+// Algorithmic bytes per row: cols * 2 * (2 + has_residual).
+
+#include "common.cuh"
+#include "host_common.h"
+
+namespace b200 {
+namespace ln {
+
+constexpr int THREADS = 256;
+constexpr int VEC = 8;         // 16-bit elements per 128-bit access
+constexpr int MAX_ITERS = 4;   // cols <= THREADS * VEC * MAX_ITERS = 8192
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int x = 16; x >= 1; x >>= 1) v += __shfl_xor_sync(0xffffffffu, v, x);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // protects `red` between consecutive reductions
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < THREADS / 32) ? red[lane] : 0.f;
+#pragma unroll
+  for (int x = 4; x >= 1; x >>= 1) t += __shfl_xor_sync(0xffffffffu, t, x);
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+template <typename T, bool HAS_RES>
+__global__ void __launch_bounds__(THREADS)
+layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, const T* __restrict__ b,
+                 T* __restrict__ y, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps, float alpha) {
+  __shared__ float red[THREADS / 32];
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * ldx;
+  const T* rr = HAS_RES ? res + row * ldr : nullptr;
+  float v[MAX_ITERS][VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < MAX_ITERS; ++it) {
+    const int c = (it * THREADS + threadIdx.x) * VEC;
+    if (c < cols) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+      float2 f;
+      f = Pack2<T>::unpack(raw.x); v[it][0] = f.x; v[it][1] = f.y;
+      f = Pack2<T>::unpack(raw.y); v[it][2] = f.x; v[it][3] = f.y;
+      f = Pack2<T>::unpack(raw.z); v[it][4] = f.x; v[it][5] = f.y;
+      f = Pack2<T>::unpack(raw.w); v[it][6] = f.x; v[it][7] = f.y;
+      if constexpr (HAS_RES) {
+        const uint4 rw = *reinterpret_cast<const uint4*>(rr + c);
+        f = Pack2<T>::unpack(rw.x); v[it][0] = fmaf(alpha, f.x, v[it][0]); v[it][1] = fmaf(alpha, f.y, v[it][1]);
+        f = Pack2<T>::unpack(rw.y); v[it][2] = fmaf(alpha, f.x, v[it][2]); v[it][3] = fmaf(alpha, f.y, v[it][3]);
+        f = Pack2<T>::unpack(rw.z); v[it][4] = fmaf(alpha, f.x, v[it][4]); v[it][5] = fmaf(alpha, f.y, v[it][5]);
+        f = Pack2<T>::unpack(rw.w); v[it][6] = fmaf(alpha, f.x, v[it][6]); v[it][7] = fmaf(alpha, f.y, v[it][7]);
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) sum += v[it][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[it][e] = 0.f;
+    }
+  }
+  const float mean = block_sum(sum, red) / static_cast<float>(cols);
+  float sq = 0.f;
+#pragma unroll
+  for (int it = 0; it < MAX_ITERS; ++it) {
+    const int c = (it * THREADS + threadIdx.x) * VEC;
+    if (c < cols) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float d = v[it][e] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / static_cast<float>(cols) + eps);
+  T* yr = y + row * ldy;
+#pragma unroll
+  for (int it = 0; it < MAX_ITERS; ++it) {
+    const int c = (it * THREADS + threadIdx.x) * VEC;
+    if (c < cols) {
+      const uint4 wr = __ldg(reinterpret_cast<const uint4*>(w + c));
+      uint4 br = make_uint4(0, 0, 0, 0);
+      if (b != nullptr) br = __ldg(reinterpret_cast<const uint4*>(b + c));
+      float o[VEC];
+      const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w}, bb[4] = {br.x, br.y, br.z, br.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 wf = Pack2<T>::unpack(ww[q]), bf = Pack2<T>::unpack(bb[q]);
+        o[2 * q] = fmaf((v[it][2 * q] - mean) * rstd, wf.x, bf.x);
+        o[2 * q + 1] = fmaf((v[it][2 * q + 1] - mean) * rstd, wf.y, bf.y);
+      }
+      uint4 pk;
+      pk.x = Pack2<T>::pack(o[0], o[1]); pk.y = Pack2<T>::pack(o[2], o[3]);
+      pk.z = Pack2<T>::pack(o[4], o[5]); pk.w = Pack2<T>::pack(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + c) = pk;
+    }
+  }
+}
+
+// narrow rows (cols <= 2048): one warp per row, 8 rows per CTA, no shared memory, shuffles only
+constexpr int W_MAX_ITERS = 8;  // cols <= 32 * VEC * W_MAX_ITERS = 2048
+
+template <typename T, bool HAS_RES>
+__global__ void __launch_bounds__(THREADS)
+layernorm_warp_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, const T* __restrict__ b,
+                      T* __restrict__ y, int64_t rows, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps,
+                      float alpha) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * ldx;
+  const T* rr = HAS_RES ? res + row * ldr : nullptr;
+  float v[W_MAX_ITERS][VEC];
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < W_MAX_ITERS; ++it) {
+    const int c = (it * 32 + lane) * VEC;
+    if (c < cols) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+      const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+      uint32_t rs[4] = {0, 0, 0, 0};
+      if constexpr (HAS_RES) {
+        const uint4 r4 = *reinterpret_cast<const uint4*>(rr + c);
+        rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = Pack2<T>::unpack(rw[q]);
+        v[it][2 * q] = f.x;
+        v[it][2 * q + 1] = f.y;
+        if constexpr (HAS_RES) {
+          const float2 g = Pack2<T>::unpack(rs[q]);
+          v[it][2 * q] = fmaf(alpha, g.x, v[it][2 * q]);
+          v[it][2 * q + 1] = fmaf(alpha, g.y, v[it][2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) sum += v[it][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) v[it][e] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int xo = 16; xo >= 1; xo >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, xo);
+  const float mean = sum / static_cast<float>(cols);
+  float sq = 0.f;
+#pragma unroll
+  for (int it = 0; it < W_MAX_ITERS; ++it) {
+    if ((it * 32 + lane) * VEC < cols) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        const float d = v[it][e] - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+  }
+#pragma unroll
+  for (int xo = 16; xo >= 1; xo >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, xo);
+  const float rstd = rsqrtf(sq / static_cast<float>(cols) + eps);
+  T* yr = y + row * ldy;
+#pragma unroll
+  for (int it = 0; it < W_MAX_ITERS; ++it) {
+    const int c = (it * 32 + lane) * VEC;
+    if (c < cols) {
+      const uint4 wr = __ldg(reinterpret_cast<const uint4*>(w + c));
+      uint4 br = make_uint4(0, 0, 0, 0);
+      if (b != nullptr) br = __ldg(reinterpret_cast<const uint4*>(b + c));
+      const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w}, bb[4] = {br.x, br.y, br.z, br.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 wf = Pack2<T>::unpack(ww[q]), bf = Pack2<T>::unpack(bb[q]);
+        pk[q] = Pack2<T>::pack(fmaf((v[it][2 * q] - mean) * rstd, wf.x, bf.x),
+                               fmaf((v[it][2 * q + 1] - mean) * rstd, wf.y, bf.y));
+      }
+      *reinterpret_cast<uint4*>(yr + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+}  // namespace ln
+}  // namespace b200
+
+extern "C" int b200_layernorm(const void* x, const void* residual, const void* weight, const void* bias, void* y,
+                              int64_t rows, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps,
+                              float residual_alpha, int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(x && weight && y, "layernorm: NULL pointer argument");
+  B200_CHECK_ARG(rows >= 0 && rows <= 0x7fffffffLL, "layernorm: bad row count");
+  B200_CHECK_ARG(cols > 0 && cols % 8 == 0 && cols <= ln::THREADS * ln::VEC * ln::MAX_ITERS,
+                 "layernorm: cols must be a multiple of 8 and <= 8192 (got %d)", cols);
+  B200_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cols && ldy >= cols && (!residual || (ldr % 8 == 0 && ldr >= cols)),
+                 "layernorm: row strides must be multiples of 8 elements and >= cols");
+  B200_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)weight & 15) == 0 &&
+                     ((uintptr_t)bias & 15) == 0 && ((uintptr_t)residual & 15) == 0,
+                 "layernorm: pointers must be 16-byte aligned");
+  B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "layernorm: dtype must be bf16 or fp16");
+  if (rows == 0) return B200_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool narrow = cols <= 32 * ln::VEC * ln::W_MAX_ITERS;
+  const unsigned grid = narrow ? static_cast<unsigned>((rows + ln::THREADS / 32 - 1) / (ln::THREADS / 32))
+                               : static_cast<unsigned>(rows);
+#define LAUNCH(T, HAS)                                                                                              \
+  if (narrow)                                                                                                          \
+    ln::layernorm_warp_kernel<T, HAS><<<grid, ln::THREADS, 0, s>>>(                                                  \
+        static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
+        static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);              \
+  else                                                                                                                 \
+    ln::layernorm_kernel<T, HAS><<<grid, ln::THREADS, 0, s>>>(                                                        \
+        static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
+        static_cast<const T*>(bias), static_cast<T*>(y), cols, ldx, ldr, ldy, eps, residual_alpha)
+  if (dtype == B200_DTYPE_BF16) {
+    if (residual) { LAUNCH(__nv_bfloat16, true); } else { LAUNCH(__nv_bfloat16, false); }
+  } else {
+    if (residual) { LAUNCH(__half, true); } else { LAUNCH(__half, false); }
+  }
+#undef LAUNCH
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}

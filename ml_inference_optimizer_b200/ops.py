@@ -359,6 +359,35 @@ def fused_mlp(x: torch.Tensor, w_up: torch.Tensor, b_up: Optional[torch.Tensor],
     return y.reshape(*lead, h_out)
 
 
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, eps: float = 1e-5,
+              residual: Optional[torch.Tensor] = None, residual_alpha: float = 1.0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``LayerNorm(x + residual_alpha * residual) * weight + bias`` over the last dimension (fp32 statistics)."""
+    dev = _require_cuda(x, weight, bias, residual, out)
+    dt = _dtype_code(x)
+    cols = x.shape[-1]
+    x2, lead = _as_rows(x)
+    r2 = None
+    if residual is not None:
+        if residual.shape != x.shape or residual.dtype != x.dtype:
+            raise ValueError("residual must match x in shape and dtype")
+        r2, _ = _as_rows(residual)
+    for t in (weight, bias):
+        if t is not None and (t.dtype != x.dtype or t.numel() != cols):
+            raise ValueError("weight / bias must be [hidden] tensors of the dtype of x")
+    weight = weight.contiguous()
+    bias = None if bias is None else bias.contiguous()
+    rows = x2.shape[0]
+    y = out.reshape(-1, cols) if out is not None else torch.empty((rows, cols), dtype=x.dtype, device=dev)
+    ld = lambda t: t.stride(0) if t.shape[0] > 1 else cols
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_layernorm(x2.data_ptr(), _ptr(r2), weight.data_ptr(), _ptr(bias), y.data_ptr(), rows, cols, ld(x2),
+                                ld(r2) if r2 is not None else 0, ld(y), float(eps), float(residual_alpha), dt, _stream_ptr(dev))
+    check("b200_layernorm", rc)
+    return y.reshape(*lead, cols)
+
+
 def set_sm_limit(max_ctas: int) -> None:
     """Cap the CTAs of the persistent GEMM kernels (0 = no cap); see ``b200_set_sm_limit``."""
     check("b200_set_sm_limit", _lib.load().b200_set_sm_limit(int(max_ctas)))

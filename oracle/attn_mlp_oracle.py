@@ -25,7 +25,7 @@ import torch
 
 __all__ = [
     "attention_ref", "decode_attention_ref", "paged_gather", "kv_append_ref", "lse_merge_ref", "mlp_ref",
-    "linear_act_ref", "gelu_tanh", "rel_err_percent", "max_abs_err", "ring_attention_ref", "tp_mlp_ref",
+    "linear_act_ref", "layernorm_ref", "gelu_tanh", "rel_err_percent", "max_abs_err", "ring_attention_ref", "tp_mlp_ref",
 ]
 
 
@@ -225,6 +225,18 @@ def mlp_ref(x, w_up, b_up, w_down, b_down, activation: str = "gelu_tanh", w_gate
     (kernels/mlp/fused_mlp.py:159-178, :262-275; kernels/triton/mlp_kernels.py:759-803)."""
     h = linear_act_ref(x, w_up, b_up, activation, w_gate, b_gate)
     return torch.nn.functional.linear(h, w_down.float(), None if b_down is None else b_down.float())
+
+
+def layernorm_ref(x, weight, bias=None, eps: float = 1e-5, residual=None, residual_alpha: float = 1.0) -> torch.Tensor:
+    """fp32 LayerNorm(x + alpha * residual) — the arithmetic of ``pytorch_layernorm``
+    (kernels/triton/layernorm_kernels.py:279-311): mean, biased variance as mean((x-u)^2), eps inside the sqrt."""
+    x = x.float()
+    if residual is not None:
+        x = x + residual_alpha * residual.float()
+    u = x.mean(dim=-1, keepdim=True)
+    s = (x - u).pow(2).mean(dim=-1, keepdim=True)
+    x = (x - u) / torch.sqrt(s + eps)
+    return weight.float() * x + (bias.float() if bias is not None else 0.0)
 
 
 def tp_mlp_ref(x, w_up, b_up, w_down, b_down, activation, tp: int, w_gate=None, b_gate=None) -> torch.Tensor:

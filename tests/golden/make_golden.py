@@ -66,6 +66,20 @@ def mlp_vectors():
     return out
 
 
+def layernorm_vectors():
+    from kernels.triton import layernorm_kernels as lk
+
+    torch.manual_seed(99)
+    x, r = torch.randn(2, 7, 96), torch.randn(2, 7, 96)
+    w, b = torch.randn(96), torch.randn(96)
+    return {
+        "pytorch_layernorm": {"x": x, "w": w, "b": b, "eps": 1e-5, "y": lk.pytorch_layernorm(x, w, b, 1e-5)},
+        "pytorch_layernorm_residual": {"x": x, "r": r, "w": w, "b": b, "eps": 1e-5, "alpha": 0.5,
+                                       "y": lk.pytorch_layernorm(x, w, b, 1e-5, r, 0.5)},
+        "pytorch_layernorm_nobias": {"x": x, "w": w, "eps": 1e-6, "y": lk.pytorch_layernorm(x, w, None, 1e-6)},
+    }
+
+
 def attention_vectors():
     # reach the PyTorch fallback of triton_ring_attention_forward: it is defined only when triton is missing
     saved = {k: sys.modules.get(k) for k in ("triton", "triton.language")}
@@ -119,7 +133,9 @@ def main():
     attn = attention_vectors()
     torch.save(mlp, os.path.join(OUT, "mlp_reference_vectors.pt"))
     torch.save(attn, os.path.join(OUT, "attention_reference_vectors.pt"))
-    for name, d in {**mlp, **attn}.items():
+    ln = layernorm_vectors()
+    torch.save(ln, os.path.join(OUT, "layernorm_reference_vectors.pt"))
+    for name, d in {**mlp, **attn, **ln}.items():
         print(f"{name}: y{tuple(d['y'].shape)} |y|max={d['y'].abs().max():.4f}")
 
 

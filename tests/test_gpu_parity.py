@@ -322,3 +322,29 @@ def test_mlp_full_size_linearity(ops):
     check_out(y_rows, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=1e-2)
     y0 = ops.fused_mlp(x[:512].contiguous(), wu, bu, torch.zeros_like(wd), bd, "swiglu", wg, bg)
     assert torch.equal(y0, bd.view(1, -1).expand(512, -1))  # zero weights: exactly the bias on every path
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm (f3)
+@pytest.mark.parametrize("rows,cols,res,bias", [(300, 768, False, True), (257, 4096, True, True), (5, 8192, True, False),
+                                                (1, 64, False, True), (1000, 1032, True, True)])
+def test_layernorm_vs_oracle(ops, rows, cols, res, bias):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g).to(torch.bfloat16)
+    x, w = r(rows, cols) * 2 + 0.5, r(cols)
+    b = r(cols) if bias else None
+    rs = r(rows, cols) if res else None
+    y = ops.layernorm(x, w, b, 1e-5, rs, 0.7)
+    c = lambda t: None if t is None else t.cpu()
+    ref = orc.layernorm_ref(c(x), c(w), c(b), 1e-5, c(rs), 0.7)
+    check_out(y, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=5e-3)
+
+
+def test_layernorm_golden_and_shim(ops, golden_dir):
+    from kernels.triton.layernorm_kernels import triton_layernorm
+
+    vecs = torch.load(os.path.join(golden_dir, "layernorm_reference_vectors.pt"))
+    d = vecs["pytorch_layernorm_residual"]
+    cu = lambda t: t.to("cuda", torch.bfloat16)
+    y = triton_layernorm(cu(d["x"]), cu(d["w"]), cu(d["b"]), d["eps"], cu(d["r"]), d["alpha"])
+    assert y.shape == d["y"].shape
+    check_out(y, d["y"], max_abs=6e-2, mean_rel=1e-2)  # inputs rounded to bf16 (|y| up to 6)

@@ -47,6 +47,16 @@ def test_pytorch_fused_mlp_functional(mlp_vecs, act):
     assert orc.max_abs_err(y, d["y"]) < 5e-5
 
 
+def test_layernorm_vs_reference(golden_dir):
+    vecs = torch.load(os.path.join(golden_dir, "layernorm_reference_vectors.pt"))
+    d = vecs["pytorch_layernorm"]
+    assert orc.max_abs_err(orc.layernorm_ref(d["x"], d["w"], d["b"], d["eps"]), d["y"]) < TOL
+    d = vecs["pytorch_layernorm_residual"]
+    assert orc.max_abs_err(orc.layernorm_ref(d["x"], d["w"], d["b"], d["eps"], d["r"], d["alpha"]), d["y"]) < TOL
+    d = vecs["pytorch_layernorm_nobias"]
+    assert orc.max_abs_err(orc.layernorm_ref(d["x"], d["w"], None, d["eps"]), d["y"]) < TOL
+
+
 def _bhsd_to_bshd(t):
     return t.permute(0, 2, 1, 3).contiguous()
 
