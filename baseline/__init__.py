@@ -1,0 +1,9 @@
+"""Drop-in import path: ``from baseline.inference import PagedKVCache, create_inference_runner`` resolves to
+``ml_inference_optimizer_b200.baseline``. (``baseline/_ref`` is a git-ignored scratch location.)"""
+import importlib
+import sys
+
+_mod = importlib.import_module("ml_inference_optimizer_b200.baseline.inference")
+sys.modules[f"{__name__}.inference"] = _mod
+inference = _mod
+from ml_inference_optimizer_b200.baseline import *  # noqa: F401,F403,E402

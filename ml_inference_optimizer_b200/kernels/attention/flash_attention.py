@@ -240,6 +240,16 @@ class FlashSelfAttention(_AttentionBase):
         return self.o_proj(ctx.reshape(B, S, self.hidden_size))
 
 
+# Paged-generation context (baseline.inference.generate_paged): HF model forwards do not carry custom keyword arguments
+# down to the attention blocks, so the adapters read the paged cache / block tables of the current step from here.
+_PAGED_CONTEXT: Optional[Dict[str, Any]] = None
+
+
+def set_paged_context(ctx: Optional[Dict[str, Any]]) -> None:
+    global _PAGED_CONTEXT
+    _PAGED_CONTEXT = ctx
+
+
 class _HFAttentionAdapter(nn.Module):
     """Stands in for a HuggingFace attention block: accepts HF's keyword arguments, returns HF's tuple, and keeps the HF
     KV cache protocol (``past_key_values.update``) so ``model.generate`` works unchanged. Prefill and cached decode
@@ -275,6 +285,22 @@ class _HFAttentionAdapter(nn.Module):
         fa = inner.flash_attention
         orig = q.dtype
         dt = fa._compute_dtype(orig)
+        if _PAGED_CONTEXT is not None:
+            ctx_ = _PAGED_CONTEXT
+            paged = ctx_["cache"]
+            if q.dtype != dt:
+                q, k, v = q.to(dt), k.to(dt), v.to(dt)
+            if ctx_["mode"] == "prefill":
+                paged.write_prefill(self.layer_idx, ctx_["seq_ids"], k, v)
+                attn = ops.flash_attn_fwd(q, k, v, causal=True, softmax_scale=inner.config.softmax_scale)
+            else:
+                kc, vc = paged.get_physical_caches()
+                ops.kv_append(k[:, 0], v[:, 0], kc, vc, ctx_["context_lengths"], ctx_["block_tables"], self.layer_idx)
+                attn = ops.decode_attention(q[:, 0].contiguous(), kc, vc, ctx_["context_lengths"],
+                                            softmax_scale=inner.config.softmax_scale, block_tables=ctx_["block_tables"],
+                                            layer_idx=self.layer_idx).unsqueeze(1)
+            out = inner.o_proj(attn.reshape(B, S, inner.hidden_size).to(orig))
+            return (out,) + (None,) * (self.returns_tuple_len - 1)
         if cache is not None and hasattr(cache, "update"):
             k_all, v_all = cache.update(k.transpose(1, 2), v.transpose(1, 2), self.layer_idx)  # [B,Hkv,Sk,D]
             k, v = k_all.transpose(1, 2), v_all.transpose(1, 2)

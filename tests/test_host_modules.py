@@ -179,3 +179,44 @@ def test_optimizer_profile_and_cpu_refusal():
     assert prof["attention_modules"] == ["transformer.h.0.attn"] and prof["mlp_modules"] == ["transformer.h.0.mlp"]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         opt.optimize()
+
+
+def test_paged_kv_cache_bookkeeping():
+    from baseline.inference import BlockManager, PagedKVCache
+
+    c = PagedKVCache(num_blocks=6, block_size=4, num_layers=2, num_heads=2, head_dim=8, dtype=torch.float32, device="cpu")
+    k, v = c.get_physical_caches()
+    assert k.shape == (6, 2, 4, 2, 8)  # [num_blocks, L, block_size, Hkv, D] (reference baseline/inference.py:1077-1084)
+    c.allocate_blocks_for_sequence(0, 6)
+    assert len(c.get_block_table(0)) == 2 and c.get_sequence_length(0) == 6
+    for _ in range(3):
+        c.append_token(0)  # 9 tokens -> third block
+    assert len(c.get_block_table(0)) == 3 and c.get_sequence_length(0) == 9
+    c.allocate_blocks_for_sequence(1, 4)
+    bt, lens = c.device_tables([0, 1])
+    assert bt.dtype == torch.int32 and bt.shape == (2, 3) and lens.tolist() == [9, 4]
+    c.allocate_blocks_for_sequence(2, 8)
+    with pytest.raises(MemoryError):
+        c.allocate_blocks_for_sequence(3, 4)  # 6 blocks exhausted
+    c.free_sequence(0)
+    assert c.block_manager.get_num_free_blocks() == 3
+    # prefill scatter lands where the block table says
+    kk = torch.arange(1 * 4 * 2 * 8, dtype=torch.float32).view(1, 4, 2, 8)
+    c.write_prefill(1, [1], kk, kk + 1)
+    blk = c.get_block_table(1)[0]
+    assert torch.equal(k[blk, 1], kk[0]) and torch.equal(v[blk, 1], kk[0] + 1) and k[blk, 0].abs().sum() == 0
+    bm = BlockManager(2, 4, 1, 1, 8, torch.float32, "cpu")
+    b0 = bm.allocate_block()
+    bm.increase_ref_count(b0)
+    bm.free_block(b0)
+    assert bm.get_num_free_blocks() == 1  # still referenced once
+    bm.free_block(b0)
+    assert bm.get_num_free_blocks() == 2
+
+
+def test_inference_runner_metrics_cpu():
+    from baseline.inference import BasicInferenceRunner
+
+    lin = torch.nn.Linear(4, 4)
+    out, metrics = BasicInferenceRunner(lin, device="cpu").run_inference(torch.randn(2, 4))
+    assert out.shape == (2, 4) and "total_time_ms" in metrics
