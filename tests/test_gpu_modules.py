@@ -212,3 +212,30 @@ def test_paged_generation_matches_cached_generation():
     # greedy tokens agree except where two logits are within bf16 noise of each other
     agree = (got == ref).float().mean().item()
     assert agree >= 0.95, agree
+
+
+def test_fused_layernorm_qkv_feeds_attention():
+    from kernels.attention.flash_attention import FlashAttention3, FlashAttentionConfig
+    from kernels.triton.fused_layernorm_qkv import flash_compatible_wrapper, ring_compatible_wrapper, triton_fused_layernorm_qkv
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).to(torch.bfloat16)
+    B, S, hid, H, Hkv, D = 2, 200, 512, 8, 2, 64
+    x, lw, lb = r(B, S, hid), r(hid), r(hid, sc=0.1)
+    wq, wk, wv = r(H * D, hid, sc=0.05), r(Hkv * D, hid, sc=0.05), r(Hkv * D, hid, sc=0.05)
+    bq = r(H * D, sc=0.1)
+    q, k, v = triton_fused_layernorm_qkv(x, lw, lb, wq, wk, wv, bq, None, None, 1e-5, H, Hkv)
+    assert q.shape == (B, S, H, D) and k.shape == (B, S, Hkv, D)
+    c = lambda t: t.float().cpu()
+    n = orc.layernorm_ref(c(x), c(lw), c(lb), 1e-5).to(torch.bfloat16).float()  # the kernel rounds the normed row to bf16
+    rq = (n @ c(wq).T + c(bq)).view(B, S, H, D)
+    rk = (n @ c(wk).T).view(B, S, Hkv, D)
+    assert rel(q, rq)[1] < 6e-2 and rel(k, rk)[1] < 6e-2
+    o = FlashAttention3(FlashAttentionConfig(causal=True, precision="bf16"))(q, k, v)  # strided views, no copies
+    ro, _ = orc.attention_ref(c(q), c(k), c(v), causal=True)
+    assert rel(o, ro)[1] < 2e-2
+    qt, kt, vt = ring_compatible_wrapper(x, lw, lb, wq, wk, wv, bq, None, None, 1e-5, H, Hkv)
+    assert qt.shape == (B, H, S, D) and torch.equal(qt.transpose(1, 2), q)
+    w3 = torch.cat([wq, r(H * D, hid, sc=0.05), r(H * D, hid, sc=0.05)])
+    q3, k3, v3 = flash_compatible_wrapper(x, lw, lb, w3, None, 1e-5, H)
+    assert q3.shape == k3.shape == (B, S, H, D) and rel(q3, (n @ c(wq).T).view(B, S, H, D))[1] < 6e-2

@@ -220,3 +220,16 @@ def test_inference_runner_metrics_cpu():
     lin = torch.nn.Linear(4, 4)
     out, metrics = BasicInferenceRunner(lin, device="cpu").run_inference(torch.randn(2, 4))
     assert out.shape == (2, 4) and "total_time_ms" in metrics
+
+
+def test_benchmark_metric_definitions():
+    from benchmarks import metrics as m
+
+    assert m.calculate_throughput(8, 128, 2.0) == 4.0
+    st = m.calculate_latency_statistics([0.1 * i for i in range(1, 101)])
+    assert abs(st["p90"] - 9.1) < 1e-9 and abs(st["p99"] - 10.0) < 1e-9 and st["min"] == 0.1
+    assert m.calculate_latency_statistics([])["mean"] == 0.0
+    assert abs(m.calculate_scaling_efficiency(118.44, 16.25, 8) - 91.1) < 0.1
+    a, b = torch.tensor([1.0, 2.0]), torch.tensor([1.1, 2.0])
+    assert abs(m.calculate_relative_error(a, b) - 5.0) < 1e-4 and abs(m.calculate_max_absolute_error(a, b) - 0.1) < 1e-6
+    assert m.calculate_relative_error(a, torch.zeros(3)) == float("inf")
