@@ -250,6 +250,210 @@ decode_kernel(const Params p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// GQA decode on the legacy tensor-core path (mma.sync m16n8k16): the G query heads that share a KV head are the M rows
+// of the MMA, so the FMA / shuffle / exp work per KV byte no longer grows with G (the CUDA-core kernel above becomes
+// ALU-bound for G >= 4). Still an HBM-streaming kernel — every K/V byte is loaded exactly once with 128-bit loads in a
+// fragment-friendly order, no shared-memory staging:
+//   Q K^T : lane (g,t) loads K[key g][32m + 8t .. +8) — the contraction (head-dim) index may be permuted freely as long
+//           as the Q fragments use the same permutation, so one uint4 feeds two k-steps (b0,b1 = words x,y then z,w);
+//   P V   : lane (g,t) loads V rows of keys {2t, 2t+1, 2t+8, 2t+9} at dims [64d + 8g, +8); PRMT pairs the two keys of a
+//           column into a B fragment. Output column n of n-tile (d, j) is dim 64d + 8n + j (undone at the final store).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  if constexpr (Pack2<T>::kIsBf16) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+}
+
+constexpr int GQA_WARPS = 4;
+
+template <int D, typename T, bool PAGED>
+__global__ void __launch_bounds__(GQA_WARPS * 32, 3)
+decode_gqa_mma_kernel(const Params p, const int G) {
+  constexpr int TILE = 16;       // keys per warp iteration
+  constexpr int MB = D / 32;     // 32-dim blocks of the head dimension (two MMA k-steps each)
+  constexpr int DG = D / 64;     // 64-dim groups of the output
+  constexpr int NT = D / 8;      // n-tiles of the P V product
+
+  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  const int ctx = p.context_lens[b];
+  int chunk = (ctx + p.splits - 1) / p.splits;
+  chunk = ((chunk + TILE - 1) / TILE) * TILE;
+  const int k_begin = min(split * chunk, ctx);
+  const int k_end = min(k_begin + chunk, ctx);
+
+  // Q fragments for rows g and g+8 (zero rows beyond the group)
+  uint32_t qa[MB][4], qb[MB][4];
+  {
+    const T* qbase = reinterpret_cast<const T*>(p.q) + (static_cast<int64_t>(b) * p.Hq + kvh * G) * D;
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      uint4 ra = make_uint4(0, 0, 0, 0), rb = make_uint4(0, 0, 0, 0);
+      if (g < G) ra = *reinterpret_cast<const uint4*>(qbase + static_cast<int64_t>(g) * D + 32 * m + 8 * t);
+      if (g + 8 < G) rb = *reinterpret_cast<const uint4*>(qbase + static_cast<int64_t>(g + 8) * D + 32 * m + 8 * t);
+      qa[m][0] = ra.x; qa[m][1] = ra.y; qa[m][2] = ra.z; qa[m][3] = ra.w;
+      qb[m][0] = rb.x; qb[m][1] = rb.y; qb[m][2] = rb.z; qb[m][3] = rb.w;
+    }
+  }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+
+  const T* kc = reinterpret_cast<const T*>(p.k_cache);
+  const T* vc = reinterpret_cast<const T*>(p.v_cache);
+  const int32_t* bt = PAGED ? p.block_table + static_cast<int64_t>(b) * p.max_blocks_per_seq : nullptr;
+  auto row_offset = [&](int key) -> int64_t {  // element offset of (key, kvh, dim 0)
+    if constexpr (PAGED) {
+      const int bi = key / p.block_size;
+      const int in_blk = key - bi * p.block_size;
+      return ((static_cast<int64_t>(bt[bi]) * p.num_layers + p.layer_idx) * p.block_size + in_blk) *
+                 (static_cast<int64_t>(p.Hkv) * D) + kvh * D;
+    } else {
+      return static_cast<int64_t>(b) * p.kv_batch_stride + static_cast<int64_t>(key) * p.kv_token_stride + kvh * D;
+    }
+  };
+
+  for (int t0 = k_begin + warp * TILE; t0 < k_end; t0 += GQA_WARPS * TILE) {
+    // ---- issue every load of the tile ----
+    uint4 kr[2][MB], vr[DG][4];
+#pragma unroll
+    for (int kg = 0; kg < 2; ++kg) {
+      const int key = t0 + kg * 8 + g;
+      const bool valid = key < k_end;
+      const int64_t off = valid ? row_offset(key) + 8 * t : 0;
+#pragma unroll
+      for (int m = 0; m < MB; ++m) kr[kg][m] = valid ? ld_stream(kc + off + 32 * m) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int key = t0 + 2 * t + (j & 1) + (j >> 1) * 8;
+      const bool valid = key < k_end;
+      const int64_t off = valid ? row_offset(key) + 8 * g : 0;
+#pragma unroll
+      for (int d = 0; d < DG; ++d) vr[d][j] = valid ? ld_stream(vc + off + 64 * d) : make_uint4(0, 0, 0, 0);
+    }
+    // ---- S = Q K^T (rows g, g+8; keys kg*8 + 2t, +1) ----
+    float sc[2][4];
+#pragma unroll
+    for (int kg = 0; kg < 2; ++kg) {
+      sc[kg][0] = sc[kg][1] = sc[kg][2] = sc[kg][3] = 0.f;
+#pragma unroll
+      for (int m = 0; m < MB; ++m) {
+        mma_16816<T>(sc[kg], qa[m][0], qb[m][0], qa[m][1], qb[m][1], kr[kg][m].x, kr[kg][m].y);
+        mma_16816<T>(sc[kg], qa[m][2], qb[m][2], qa[m][3], qb[m][3], kr[kg][m].z, kr[kg][m].w);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = t0 + kg * 8 + 2 * t + (e & 1);
+        sc[kg][e] = key < k_end ? sc[kg][e] * p.scale_log2 : -INFINITY;
+      }
+    }
+    // ---- online softmax for the two rows this lane holds ----
+    float pr[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float tmax = fmaxf(fmaxf(sc[0][2 * r], sc[0][2 * r + 1]), fmaxf(sc[1][2 * r], sc[1][2 * r + 1]));
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+      const float m_new = fmaxf(m_run[r], tmax);
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = fast_exp2(m_run[r] - m_safe);
+      m_run[r] = m_new;
+      l_run[r] *= corr;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { o[n][2 * r] *= corr; o[n][2 * r + 1] *= corr; }
+#pragma unroll
+      for (int kg = 0; kg < 2; ++kg) {
+        pr[kg][2 * r] = fast_exp2(sc[kg][2 * r] - m_safe);
+        pr[kg][2 * r + 1] = fast_exp2(sc[kg][2 * r + 1] - m_safe);
+        l_run[r] += pr[kg][2 * r] + pr[kg][2 * r + 1];
+      }
+    }
+    // ---- O += P V ----
+    const uint32_t pa0 = Pack2<T>::pack(pr[0][0], pr[0][1]), pa1 = Pack2<T>::pack(pr[0][2], pr[0][3]);
+    const uint32_t pa2 = Pack2<T>::pack(pr[1][0], pr[1][1]), pa3 = Pack2<T>::pack(pr[1][2], pr[1][3]);
+#pragma unroll
+    for (int d = 0; d < DG; ++d) {
+      const uint32_t w0[4] = {vr[d][0].x, vr[d][0].y, vr[d][0].z, vr[d][0].w};
+      const uint32_t w1[4] = {vr[d][1].x, vr[d][1].y, vr[d][1].z, vr[d][1].w};
+      const uint32_t w2[4] = {vr[d][2].x, vr[d][2].y, vr[d][2].z, vr[d][2].w};
+      const uint32_t w3[4] = {vr[d][3].x, vr[d][3].y, vr[d][3].z, vr[d][3].w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+        const uint32_t b0 = __byte_perm(w0[j >> 1], w1[j >> 1], sel);  // (V[key 2t][dim], V[key 2t+1][dim])
+        const uint32_t b1 = __byte_perm(w2[j >> 1], w3[j >> 1], sel);  // (V[key 2t+8][dim], V[key 2t+9][dim])
+        mma_16816<T>(o[d * 8 + j], pa0, pa1, pa2, pa3, b0, b1);
+      }
+    }
+  }
+
+  // ---- combine: lanes of a row quad, then the warps of the CTA through shared memory ----
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  __shared__ float sm_m[GQA_WARPS][16];
+  __shared__ float sm_l[GQA_WARPS][16];
+  __shared__ float sm_acc[GQA_WARPS][16][D];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = g + 8 * r;
+    if (row < G) {
+      if (t == 0) { sm_m[warp][row] = m_run[r]; sm_l[warp][row] = l_run[r]; }
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int d = n >> 3, j = n & 7;
+        sm_acc[warp][row][64 * d + 8 * (2 * t) + j] = o[n][2 * r];
+        sm_acc[warp][row][64 * d + 8 * (2 * t + 1) + j] = o[n][2 * r + 1];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < G * D; idx += GQA_WARPS * 32) {
+    const int row = idx / D, d = idx - row * D;
+    float m = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < GQA_WARPS; ++w) m = fmaxf(m, sm_m[w][row]);
+    const float m_safe = (m == -INFINITY) ? 0.f : m;
+    float l = 0.f, acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < GQA_WARPS; ++w) {
+      const float c = fast_exp2(sm_m[w][row] - m_safe);
+      l = fmaf(sm_l[w][row], c, l);
+      acc = fmaf(sm_acc[w][row][d], c, acc);
+    }
+    const float out = l > 0.f ? acc / l : 0.f;
+    const float lse = l > 0.f ? (m + log2f(l)) * kLn2 : -INFINITY;
+    const int h = kvh * G + row;
+    if (p.splits == 1) {
+      T* op = reinterpret_cast<T*>(p.o) + (static_cast<int64_t>(b) * p.Hq + h) * D + d;
+      if constexpr (Pack2<T>::kIsBf16) *op = __float2bfloat16_rn(out);
+      else *op = __float2half_rn(out);
+      if (d == 0 && p.lse != nullptr) p.lse[static_cast<int64_t>(b) * p.Hq + h] = lse;
+    } else {
+      const int64_t prow = (static_cast<int64_t>(b) * p.Hq + h) * p.splits + split;
+      p.part_o[prow * D + d] = out;
+      if (d == 0) p.part_lse[prow] = lse;
+    }
+  }
+}
+
 // merge the per-split partials: o = sum_s exp(lse_s - lse) o_s
 template <int D, typename T>
 __global__ void decode_reduce_kernel(const float* __restrict__ part_o, const float* __restrict__ part_lse,
@@ -383,14 +587,29 @@ int launch_decode(const Params& p, bool paged, cudaStream_t stream) {
 }
 
 template <int D, typename T>
+int launch_decode_gqa(int G, const Params& p, bool paged, cudaStream_t stream) {
+  dim3 grid(p.splits, p.Hkv, p.B);
+  if (paged) decode_gqa_mma_kernel<D, T, true><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
+  else decode_gqa_mma_kernel<D, T, false><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
+  B200_CUDA_OK(cudaGetLastError());
+  if (p.splits > 1) {
+    decode_reduce_kernel<D, T><<<p.B * p.Hq, D, 0, stream>>>(p.part_o, p.part_lse, p.o, p.lse, p.splits);
+    B200_CUDA_OK(cudaGetLastError());
+  }
+  return B200_OK;
+}
+
+template <int D, typename T>
 int dispatch_group(int G, const Params& p, bool paged, cudaStream_t stream) {
+  // wide groups: the query heads of a KV head become the rows of mma.sync tiles (any G up to 16)
+  if (G >= 3 && G <= 16) return launch_decode_gqa<D, T>(G, p, paged, stream);
   switch (G) {
     case 1: return launch_decode<D, 1, T>(p, paged, stream);
     case 2: return launch_decode<D, 2, T>(p, paged, stream);
     case 4: return launch_decode<D, 4, T>(p, paged, stream);
     case 8: return launch_decode<D, 8, T>(p, paged, stream);
     default:
-      return set_error(B200_ERR_UNSUPPORTED, "decode: Hq/Hkv = %d is not supported (1, 2, 4, 8)", G);
+      return set_error(B200_ERR_UNSUPPORTED, "decode: Hq/Hkv = %d is not supported (1 .. 16)", G);
   }
 }
 
@@ -403,7 +622,9 @@ int b200_fa_decode_num_splits(int B, int Hkv, int max_context_len) {
   if (B <= 0 || Hkv <= 0 || max_context_len <= 0) return 1;
   const int sms = b200::sm_count();
   const int64_t ctas = static_cast<int64_t>(B) * Hkv;
-  const int64_t target = 3LL * sms;  // ~3 resident CTAs per SM
+  // 2-3 CTAs are resident per SM; aim for >= 4 waves so that the partial last wave costs little (a 1.15-wave launch
+  // left the GQA decode at 58% of the bandwidth it reaches with 4 splits)
+  const int64_t target = 12LL * sms;
   int splits = static_cast<int>((target + ctas - 1) / ctas);
   const int max_by_len = (max_context_len + 255) / 256;  // keep >= 256 keys per split
   if (splits > max_by_len) splits = max_by_len;

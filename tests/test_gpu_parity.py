@@ -175,6 +175,10 @@ DECODE_CASES = [
     (2, 8, 1, 64, 700, 2),
     (1, 32, 8, 128, 8192, 0),   # Llama-3 GQA, long context, small batch -> many splits
     (2, 12, 12, 64, 129, 4),    # GPT-2 heads, more splits than 64-key tiles in some batches
+    (2, 12, 4, 128, 500, 0),    # G = 3 (tensor-core GQA path, rows padded to 16)
+    (2, 40, 8, 128, 700, 3),    # G = 5
+    (1, 16, 1, 64, 333, 2),     # MQA with 16 query heads: all 16 MMA rows live
+    (3, 16, 2, 128, 17, 1),     # G = 8, context shorter than two tiles
 ]
 
 
