@@ -16,6 +16,8 @@
 // loads (rows of W_gate, rows of W_up) and one N=256 MMA computes both; the epilogue reads matching gate/up
 // columns, applies silu(g)*u and emits a 128x128 output tile. The [T, i] gate and up tensors never exist.
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -49,6 +51,7 @@ struct Params {
   float* partial;
   void* y;       // output pointer / row stride for the split-K reduce pass
   int64_t ldy;
+  int use_pair;  // CTA-pair kernel (M = 256 tiles): num_m_blocks counts 256-row blocks
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int tile_in, int& m_blk, int& n_blk, int& kb0, int& kb1) {
@@ -395,9 +398,257 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap& tb1
   return B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05.mma cta_group::2, M = 256): each CTA stages its own 128 rows of A and HALF of
+// the B tile (128 of the 256 accumulator columns' weight rows); one MMA issued by the leader CTA reads both SMs' shared
+// memory, so every weight byte is fetched into shared memory once per 256 output rows instead of once per 128. Per CTA
+// and k-block that is 32 KB instead of 48 KB of TMA traffic / shared-memory fill, which buys two more pipeline stages
+// (6 x 32 KB) and less power under the 1 kW cap. Each CTA keeps its 128 x 256 fp32 accumulator (double buffered) in its
+// own TMEM and runs the same fused epilogue. SwiGLU falls out naturally: CTA 0 stages the gate rows, CTA 1 the up rows.
+// ---------------------------------------------------------------------------------------------------------------
+namespace pair {
+constexpr int P_STAGES = 6;
+constexpr int P_A_STAGE_BYTES = 128 * BK * 2;  // 16 KB
+constexpr int P_B_STAGE_BYTES = 128 * BK * 2;  // 16 KB: this CTA's half of the 256-column B tile
+constexpr int P_SMEM_A_OFF = 0;
+constexpr int P_SMEM_B_OFF = P_SMEM_A_OFF + P_STAGES * P_A_STAGE_BYTES;
+constexpr int P_SMEM_C_OFF = P_SMEM_B_OFF + P_STAGES * P_B_STAGE_BYTES;
+constexpr int P_SMEM_BAR_OFF = P_SMEM_C_OFF + 2 * C_BUF_BYTES;
+constexpr int P_SMEM_BYTES = P_SMEM_BAR_OFF + 256 + 1024;
+}  // namespace pair
+
+template <int ACT, typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
+                     const __grid_constant__ CUtensorMap tmap_b1, const __grid_constant__ CUtensorMap tmap_c,
+                     const Params p) {
+  using namespace pair;
+  constexpr bool kSwiglu = (ACT == B200_ACT_SWIGLU);
+  constexpr int OUT_COLS = kSwiglu ? 128 : 256;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_SMEM_BAR_OFF);
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + P_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs)
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b0);
+    tma_prefetch_desc(&tmap_b1);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // only the leader's is used: one arrive.expect_tx, bytes of both CTAs
+      mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit from the leader
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);   // multicast tcgen05.commit from the leader
+      mbar_init(&tmem_empty_bar[s], 2);  // leader's: one elected arrival per CTA of the pair
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_2sm(tmem_ptr_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // p.num_m_blocks counts 256-row blocks for this kernel
+  auto coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int per_group = (GROUP_M / 2) * p.num_n_blocks;
+    const int group = tile / per_group;
+    const int first_m = group * (GROUP_M / 2);
+    const int rows_in_group = min(GROUP_M / 2, p.num_m_blocks - first_m);
+    const int in_group = tile - group * per_group;
+    m_blk = first_m + in_group % rows_in_group;
+    n_blk = in_group / rows_in_group;
+  };
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < p.num_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        coords(tile, m_blk, n_blk);
+        const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
+        const int n0 = n_blk * OUT_COLS;
+        const CUtensorMap* tb = (kSwiglu && rank == 1) ? &tmap_b1 : &tmap_b0;     // SwiGLU: CTA0 gate rows, CTA1 up rows
+        const int brow = kSwiglu ? n0 : n0 + static_cast<int>(rank) * 128;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (P_A_STAGE_BYTES + P_B_STAGE_BYTES));
+          tma_load_2d_2sm(smem + P_SMEM_A_OFF + stage * P_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
+          tma_load_2d_2sm(smem + P_SMEM_B_OFF + stage * P_B_STAGE_BYTES, tb, &full_bar[stage], kb * BK, brow);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN, Pack2<T>::kIsBf16, false, false);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem + P_SMEM_A_OFF), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem + P_SMEM_B_OFF), 16, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < p.num_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * (P_A_STAGE_BYTES >> 4));
+          const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * (P_B_STAGE_BYTES >> 4));
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_ss_2sm(d_tmem, ad + static_cast<uint64_t>(k * 2), bd + static_cast<uint64_t>(k * 2), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 0x3);  // frees the stage in both CTAs
+          }
+          __syncwarp();
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ep_warp = warp_idx - 4;
+    const int ep_tid = threadIdx.x - 128;
+    const int row = ep_warp * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(ep_warp * 32) << 16;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cbuf = 0;
+    for (int tile = pair_id; tile < p.num_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      coords(tile, m_blk, n_blk);
+      const int m0 = m_blk * 256 + static_cast<int>(rank) * 128;
+      const int n0 = n_blk * OUT_COLS;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int chunk = 0; chunk < OUT_COLS / 64; ++chunk) {
+        uint8_t* cs = smem + P_SMEM_C_OFF + cbuf * C_BUF_BYTES;
+        if (ep_tid == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int col = chunk * 64 + half * 32;
+          uint32_t v[32];
+          float f[32];
+          if constexpr (kSwiglu) {
+            uint32_t u[32];
+            tmem_ld_x32(t_acc + col, v);
+            tmem_ld_x32(t_acc + 128 + col, u);
+            tmem_wait_ld();
+            float bg[32], bu[32];
+            load_bias32<T>(p.bias0, n0 + col, p.N_out, bg);
+            load_bias32<T>(p.bias1, n0 + col, p.N_out, bu);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = silu(__uint_as_float(v[i]) + bg[i]) * (__uint_as_float(u[i]) + bu[i]);
+          } else {
+            tmem_ld_x32(t_acc + col, v);
+            tmem_wait_ld();
+            float b[32];
+            load_bias32<T>(p.bias0, n0 + col, p.N_out, b);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = apply_act<ACT>(__uint_as_float(v[i]) + b[i]);
+          }
+          if (chunk == OUT_COLS / 64 - 1 && half == 1) {
+            // all TMEM reads of this accumulator stage are done in this CTA: one elected arrival on the leader's barrier
+            tc_fence_before();
+            named_bar_sync(2, 128);
+            if (ep_tid == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 pk;
+            pk.x = Pack2<T>::pack(f[q * 8 + 0], f[q * 8 + 1]);
+            pk.y = Pack2<T>::pack(f[q * 8 + 2], f[q * 8 + 3]);
+            pk.z = Pack2<T>::pack(f[q * 8 + 4], f[q * 8 + 5]);
+            pk.w = Pack2<T>::pack(f[q * 8 + 6], f[q * 8 + 7]);
+            const int c16 = half * 4 + q;
+            *reinterpret_cast<uint4*>(cs + row * 128 + ((c16 ^ (row & 7)) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (ep_tid == 0) {
+          tma_store_2d(&tmap_c, cs, n0 + chunk * 64, m0);
+          tma_store_commit();
+        }
+        cbuf ^= 1;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (ep_tid == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory / barriers are referenced until the very end
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <int ACT, typename T>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap& tb1, const CUtensorMap& tc, const Params& p,
+                cudaStream_t stream) {
+  auto kern = gemm_act_pair_kernel<ACT, T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pair::P_SMEM_BYTES));
+    attr_set = true;
+  }
+  int max_ctas = sm_count();
+  if (sm_limit() > 0 && sm_limit() < max_ctas) max_ctas = sm_limit();
+  int pairs = max_ctas / 2;
+  if (pairs > p.num_tiles) pairs = p.num_tiles;
+  if (pairs < 1) pairs = 1;
+  kern<<<2 * pairs, NUM_THREADS, pair::P_SMEM_BYTES, stream>>>(ta, tb0, tb1, tc, p);
+  B200_CUDA_OK(cudaGetLastError());
+  return B200_OK;
+}
+
 template <typename T>
 int dispatch(int act, const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap& tb1, const CUtensorMap& tc,
              const Params& p, cudaStream_t stream) {
+  if (p.use_pair) {
+    switch (act) {
+      case B200_ACT_NONE: return launch_pair<B200_ACT_NONE, T>(ta, tb0, tb1, tc, p, stream);
+      case B200_ACT_GELU_TANH: return launch_pair<B200_ACT_GELU_TANH, T>(ta, tb0, tb1, tc, p, stream);
+      case B200_ACT_GELU_ERF: return launch_pair<B200_ACT_GELU_ERF, T>(ta, tb0, tb1, tc, p, stream);
+      case B200_ACT_RELU: return launch_pair<B200_ACT_RELU, T>(ta, tb0, tb1, tc, p, stream);
+      case B200_ACT_SWIGLU: return launch_pair<B200_ACT_SWIGLU, T>(ta, tb0, tb1, tc, p, stream);
+      default: return set_error(B200_ERR_INVALID_ARGUMENT, "unknown activation %d", act);
+    }
+  }
   switch (act) {
     case B200_ACT_NONE: return launch<B200_ACT_NONE, T>(ta, tb0, tb1, tc, p, stream);
     case B200_ACT_GELU_TANH: return launch<B200_ACT_GELU_TANH, T>(ta, tb0, tb1, tc, p, stream);
@@ -502,6 +753,10 @@ int linear_act_impl(const void* x, int64_t ldx, const void* w, const void* b, co
     p.k_splits = choose_k_splits(p.num_m_blocks * p.num_n_blocks, p.num_k_blocks);
     p.partial = static_cast<float*>(workspace);
   }
+  // large problems: CTA-pair kernel (256-row tiles). B200_GEMM_PAIR=0 in the environment keeps the single-CTA kernel.
+  static const bool pair_enabled = [] { const char* e = getenv("B200_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  p.use_pair = (pair_enabled && p.k_splits == 1 && T >= 1024) ? 1 : 0;
+  if (p.use_pair) p.num_m_blocks = (p.M + 255) / 256;
   p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
   p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.num_tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
