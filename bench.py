@@ -252,25 +252,50 @@ def run_ours(args, w):
     attn_ms = elapsed_ms / args.steps - gemm1_ms - gemm2_ms
 
     # ---- e2e: host buffers through the public API, copies inside the timed region ----
+    # Every step moves its inputs pinned-host -> device and both results device -> host. The three stages run on three
+    # streams over a double-buffered set of device tensors (as a serving loop would): the H2D of step s+1 and the D2H of
+    # step s-1 overlap the kernels of step s; PCIe is full duplex.
     pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
     hq, hk, hv, hx = pin(q), pin(k), pin(v), pin(x)
     ho = torch.empty(o.shape, dtype=bf, pin_memory=True)
     hy = torch.empty(y.shape, dtype=bf, pin_memory=True)
+    sets = [(q, k, v, x, o, y), tuple(torch.empty_like(t) for t in (q, k, v, x, o, y))]
+    s_h2d, s_cmp, s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
-    def e2e_step():
-        q.copy_(hq, non_blocking=True); k.copy_(hk, non_blocking=True); v.copy_(hv, non_blocking=True)
-        x.copy_(hx, non_blocking=True)
-        ops.flash_attn_fwd(q, k, v, causal=True, out=o)
-        ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg, out=y)
-        ho.copy_(o, non_blocking=True); hy.copy_(y, non_blocking=True)
+    def e2e_run(n_steps):
+        h2d_done, cmp_done, d2h_done = {}, {}, {}
+        for st in range(n_steps):
+            dq, dk, dv, dx, do, dy = sets[st % 2]
+            with torch.cuda.stream(s_h2d):
+                if st >= 2:
+                    s_h2d.wait_event(cmp_done[st - 2])  # the kernels of step st-2 have consumed this input set
+                dq.copy_(hq, non_blocking=True); dk.copy_(hk, non_blocking=True); dv.copy_(hv, non_blocking=True)
+                dx.copy_(hx, non_blocking=True)
+                h2d_done[st] = torch.cuda.Event(); h2d_done[st].record(s_h2d)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(h2d_done[st])
+                if st >= 2:
+                    s_cmp.wait_event(d2h_done[st - 2])  # the results of step st-2 have left this output set
+                ops.flash_attn_fwd(dq, dk, dv, causal=True, out=do)
+                ops.fused_mlp(dx, wu, bu, wd, bd, act, wg, bg, out=dy)
+                cmp_done[st] = torch.cuda.Event(); cmp_done[st].record(s_cmp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(cmp_done[st])
+                ho.copy_(do, non_blocking=True); hy.copy_(dy, non_blocking=True)
+                d2h_done[st] = torch.cuda.Event(); d2h_done[st].record(s_d2h)
+        for st_ in (s_h2d, s_cmp, s_d2h):
+            torch.cuda.current_stream(dev).wait_stream(st_)
 
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    e2e_steps = max(4, min(args.steps, 10))
+    e2e_run(2)
     barrier()
     s2, e2 = ev(), ev()
+    for st_ in (s_h2d, s_cmp, s_d2h):
+        st_.wait_stream(torch.cuda.current_stream(dev))
     s2.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for st_ in (s_h2d, s_cmp, s_d2h):
+        st_.wait_event(s2)
+    e2e_run(e2e_steps)
     e2.record()
     barrier()
     e2e_ms = s2.elapsed_time(e2)
@@ -311,7 +336,8 @@ def run_ours(args, w):
                          "traffic": 3.872766e9 if args.workload == "c3" else None,
                          "other_kernels_ms": {"fa_fwd_kernel": attn_ms, "gemm_act_kernel<none> (down projection)": gemm2_ms}},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / e2e_steps},
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "pipeline": "3 streams (H2D / kernels / D2H), double-buffered device tensors, pinned host buffers"},
             "gpu_launches": 3 * args.steps,
             "clocks": clocks,
         }
