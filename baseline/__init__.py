@@ -6,4 +6,7 @@ import sys
 _mod = importlib.import_module("ml_inference_optimizer_b200.baseline.inference")
 sys.modules[f"{__name__}.inference"] = _mod
 inference = _mod
+_mu = importlib.import_module("ml_inference_optimizer_b200.baseline.model_utils")
+sys.modules[f"{__name__}.model_utils"] = _mu
+model_utils = _mu
 from ml_inference_optimizer_b200.baseline import *  # noqa: F401,F403,E402

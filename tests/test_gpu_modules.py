@@ -239,3 +239,38 @@ def test_fused_layernorm_qkv_feeds_attention():
     w3 = torch.cat([wq, r(H * D, hid, sc=0.05), r(H * D, hid, sc=0.05)])
     q3, k3, v3 = flash_compatible_wrapper(x, lw, lb, w3, None, 1e-5, H)
     assert q3.shape == k3.shape == (B, S, H, D) and rel(q3, (n @ c(wq).T).view(B, S, H, D))[1] < 6e-2
+
+
+def test_add_paged_attention_to_model_and_benchmark_runner(tmp_path):
+    """Rows f1/f4: ``add_paged_attention_to_model`` leaves the input model untouched, the copy generates through the
+    paged cache; the reference-shaped benchmark runner reports its keys for the baseline and optimised variants."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from baseline.inference import PagedKVCache
+    from baseline.model_utils import add_paged_attention_to_model
+    from benchmarks.runners import BenchmarkConfig, ModelBenchmarkRunner
+
+    torch.manual_seed(0)
+    cfg = GPT2Config(n_layer=2, attn_implementation="eager")
+    model = GPT2LMHeadModel(cfg).eval().to("cuda", torch.bfloat16)
+    ids = torch.randint(0, cfg.vocab_size, (2, 33), device="cuda")
+    paged = add_paged_attention_to_model(model)
+    assert type(model.transformer.h[0].attn).__name__ == "GPT2Attention"  # original untouched (reference deep-copies)
+    cache = PagedKVCache(num_blocks=12, block_size=16, num_layers=2, num_heads=12, head_dim=64, dtype=torch.bfloat16,
+                         device="cuda")
+    paged.set_paged_kv_cache(cache)
+    got = paged.generate_paged(ids, 6)
+    ref = model.generate(ids, max_new_tokens=6, do_sample=False, pad_token_id=0)
+    assert got.shape == ref.shape and (got == ref).float().mean().item() >= 0.95
+    assert cache.get_sequence_length(1) == 33 + 5
+
+    bc = BenchmarkConfig("gpt2-2l", [2], [128], ["baseline", "optimized"], num_iterations=5, warmup_iterations=2,
+                         precision="bf16", save_results=True, validate_outputs=False)
+    runner = ModelBenchmarkRunner(bc, lambda: GPT2LMHeadModel(cfg), results_dir=str(tmp_path))
+    res = runner.run_benchmarks()["benchmarks"]["bs2_seq128"]
+    for variant in ("baseline", "optimized"):
+        for key in ("avg_latency_ms", "throughput_samples_per_sec", "latency_p50_ms", "latency_p99_ms", "memory_usage_mb",
+                    "tokens_per_second", "batch_size", "sequence_length"):
+            assert key in res[variant], (variant, key)
+        assert res[variant]["avg_latency_ms"] > 0
+    assert any(f.endswith("_gpt2-2l.json") for f in os.listdir(tmp_path))

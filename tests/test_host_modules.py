@@ -233,3 +233,38 @@ def test_benchmark_metric_definitions():
     a, b = torch.tensor([1.0, 2.0]), torch.tensor([1.1, 2.0])
     assert abs(m.calculate_relative_error(a, b) - 5.0) < 1e-4 and abs(m.calculate_max_absolute_error(a, b) - 0.1) < 1e-6
     assert m.calculate_relative_error(a, torch.zeros(3)) == float("inf")
+
+
+def test_benchmark_runner_host_logic(tmp_path):
+    """Row f4: the runner keeps the reference's config defaults, result tree, validation rules and JSON export
+    (reference benchmarks/runners.py:28-50, :250-330); timing itself needs a GPU and fails loudly on CPU inputs."""
+    from benchmarks.runners import BenchmarkConfig, BenchmarkRunner, ModelBenchmarkRunner
+
+    cfg = BenchmarkConfig("toy", [1], [8], ["baseline"], save_results=False)
+    assert cfg.devices == ["cuda:0"] and cfg.num_iterations == 100 and cfg.warmup_iterations == 10
+    assert cfg.to_dict()["precision"] == "fp16"
+    r = BenchmarkRunner(cfg, results_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        BenchmarkRunner(BenchmarkConfig("toy", [1], [8], [], precision="int3", save_results=False))
+    with pytest.raises(NotImplementedError):
+        r.setup_model_variants()
+    a = torch.arange(6.0).view(2, 3)
+    assert r.validate_model_outputs(a, a + 1e-5)
+    assert not r.validate_model_outputs(a, a + 1.0)
+    assert r.validate_model_outputs((a, a), (a, a)) and not r.validate_model_outputs((a,), (a, a))
+    assert r.validate_model_outputs({"logits": a}, {"logits": a}) and not r.validate_model_outputs("x", "x")
+    path = r.save_benchmark_results({"t": a, "nested": {"v": (a, 1)}}, "out.json")
+    import json
+    assert json.load(open(path))["nested"]["v"][1] == 1
+    with pytest.raises(RuntimeError):
+        r.measure_performance(torch.nn.Identity(), {"input": torch.zeros(1, 4)})
+    m = ModelBenchmarkRunner(BenchmarkConfig("toy", [2], [8], ["nonsense"], save_results=False), lambda: torch.nn.Linear(2, 2))
+    ids = m.generate_test_inputs(2, 8)["input_ids"]
+    assert ids.shape == (2, 8) and torch.equal(ids, m.generate_test_inputs(2, 8)["input_ids"])
+
+
+def test_add_paged_attention_requires_attention_layers():
+    from baseline.model_utils import add_paged_attention_to_model
+
+    with pytest.raises(ValueError):
+        add_paged_attention_to_model(torch.nn.Sequential(torch.nn.Linear(4, 4)))
