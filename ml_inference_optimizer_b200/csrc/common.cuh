@@ -114,6 +114,85 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Variants taking a 32-bit shared-window address. A hot loop that is short of registers makes the compiler
+// rematerialise `smem_u32(ptr)` (generic->shared conversion: two S2R plus the alignment arithmetic) in front of every
+// barrier operation; an address kept in one opaque register (`smem_addr_opaque`) plus a constant offset avoids that.
+__device__ __forceinline__ uint32_t smem_addr_opaque(const void* p) {
+  uint32_t a;
+  asm volatile("mov.u32 %0, %1;" : "=r"(a) : "r"(smem_u32(p)));
+  return a;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > B200_MBAR_SPIN_LIMIT) {
+      printf("b200: mbarrier wait timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+
+// Wait that may legitimately last as long as a whole work item of a persistent CTA (milliseconds): back off between
+// polls; the bound (seconds) still turns a protocol bug into a trap.
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) {
+      printf("b200: mbarrier long-wait timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// ---- cluster launch control (sm_100): a running CTA takes over the block index of a not-yet-launched CTA of its own
+// grid. The 16-byte response lands in shared memory through the async proxy and completes 16 tx bytes on `bar`. ----
+__device__ __forceinline__ void clc_try_cancel(void* response16, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                   smem_u32(response16)),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+// Returns true and the stolen block index when the request succeeded; false = no blocks left (do not ask again).
+__device__ __forceinline__ bool clc_query(const void* response16, int& x, int& y, int& z) {
+  uint32_t ok, rx, ry, rz;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      ".reg .b128 R;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "mov.u32 %1, 0;\n\t"
+      "mov.u32 %2, 0;\n\t"
+      "ld.shared.b128 R, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 P, R;\n\t"
+      "selp.u32 %3, 1, 0, P;\n\t"
+      "@P clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, R;\n\t"
+      "}\n"
+      : "=&r"(rx), "=&r"(ry), "=&r"(rz), "=&r"(ok)
+      : "r"(smem_u32(response16))
+      : "memory");
+  x = static_cast<int>(rx);
+  y = static_cast<int>(ry);
+  z = static_cast<int>(rz);
+  return ok != 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — loads complete on an mbarrier, stores use bulk groups
 // ---------------------------------------------------------------------------------------------
@@ -308,6 +387,57 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
+// Predicated forms: executed by the whole (converged) warp, the instruction itself is guarded by `issue` (true in
+// one elected lane). Without a divergent branch around the issue code the compiler keeps the descriptor arithmetic
+// in the uniform datapath instead of computing it per lane and moving it over with R2UR right before every MMA.
+__device__ __forceinline__ uint32_t elect_one_u32() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_ss_if(uint32_t issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_if(uint32_t issue, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t issue, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMEM <-> registers. Shape 32x32b: thread i of the warp owns TMEM lane (32*(warp%4) + i) and receives
 // N consecutive 32-bit columns.
@@ -323,6 +453,12 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+
+__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
@@ -364,6 +500,13 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Same instruction, but pinned in program order relative to other volatile asm (tcgen05.ld/st, mbarrier ops): used
+// where the position of the exponentials relative to a TMEM store is part of the pipeline design.
+__device__ __forceinline__ float fast_exp2_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float fast_tanh(float x) {

@@ -47,21 +47,20 @@ struct Cfg {
   static constexpr int SMEM_KV_OFF = 2 * TILE_BYTES;
   static constexpr int SMEM_BAR_OFF = SMEM_KV_OFF + KV_STAGES * TILE_BYTES;
   static constexpr int SMEM_BYTES = SMEM_BAR_OFF + 512 + 1024;
-  // D = 128 fills TMEM: [S0 | S1 | O0 | O1], P_t overlays the upper half of S_t, so Q_t K(j+1)^T has to wait for P_t(j) V(j).
-  // D = 64 leaves room for separate P buffers: [S0 | S1 | P0 | P1 | O0 | O1]; S_t is free as soon as the softmax warps
-  // have read it, so the next Q K^T can be issued during the exponentials ("decoupled" pipeline, -DB200_FA_DECOUPLE).
-#ifdef B200_FA_DECOUPLE
-  static constexpr bool DECOUPLED = (D == 64);
-#else
-  static constexpr bool DECOUPLED = false;  // measured: both tiles then run in lockstep and share the MUFU pipe (606 vs 701 TFLOP/s)
+  // TMEM (512 columns): [S0 | S1 | O0 | O1]; P_t (16 bit) overlays the upper half of S_t, so Q_t K(j+1)^T is ordered
+  // behind P_t(j) V(j) on the tensor pipe. (Separate P buffers for D = 64 were measured slower: both tiles then run
+  // in lockstep and share the MUFU pipe, 606 vs 701 TFLOP/s.)
+  static constexpr uint32_t TMEM_S = 0;    // + t * 128
+#ifndef B200_FA_TMEM_P
+#define B200_FA_TMEM_P 64
 #endif
-  static constexpr uint32_t TMEM_S = 0;                          // + t * 128
-  static constexpr uint32_t TMEM_P = DECOUPLED ? 256 : 64;       // + t * (DECOUPLED ? 64 : 128)
-  static constexpr uint32_t TMEM_P_STRIDE = DECOUPLED ? 64 : 128;
-  static constexpr uint32_t TMEM_O = DECOUPLED ? 384 : 256;      // + t * D
+  static constexpr uint32_t TMEM_P = B200_FA_TMEM_P;  // + t * 128
+  static constexpr uint32_t TMEM_O = 256;  // + t * D
 };
 
 struct Params {
+  void* o;                  // output, addressed by element strides (batch, seq, head); head dim contiguous
+  int64_t o_sb, o_ss, o_sh;
   float* lse;               // [B, Hq, Sq] or nullptr
   const int32_t* kv_lens;   // [B] or nullptr
   int B, Sq, Sk, Hq, Hkv;
@@ -69,6 +68,7 @@ struct Params {
   int causal;
   int64_t causal_offset;    // key j visible to query i iff j <= i + causal_offset
   int num_pairs;            // ceil(Sq / 256)
+  int persistent;           // 1: a CTA that finished its block steals further blocks (cluster launch control)
 };
 
 // number of KV tiles a query tile [row0, row0+128) needs
@@ -84,59 +84,88 @@ __device__ __forceinline__ int num_kv_tiles(const Params& p, int row0, int kv_le
   return static_cast<int>((visible + BLOCK_N - 1) / BLOCK_N);
 }
 
+// One work item = one block index of the launch grid: a pair of 128-row query tiles of one (batch, head).
+struct Work {
+  int head, batch, kv_head, q_row0, kv_len, n0, n1, n_max;
+  __device__ __forceinline__ void set(const Params& p, int bx, int by, int bz) {
+    // heavy (late) query tiles first under a causal mask
+    const int pair = p.causal ? (p.num_pairs - 1 - bx) : bx;
+    head = by;
+    batch = bz;
+    kv_head = head / (p.Hq / p.Hkv);
+    q_row0 = pair * 2 * BLOCK_M;
+    kv_len = p.Sk;
+    if (p.kv_lens != nullptr) kv_len = max(0, min(p.Sk, p.kv_lens[batch]));
+    n0 = num_kv_tiles(p, q_row0, kv_len);
+    n1 = num_kv_tiles(p, q_row0 + BLOCK_M, kv_len);
+    n_max = max(n0, n1);
+  }
+  // Every lane holds the same values, but the compiler cannot know that for fields derived from a launch-control
+  // response or a global load; broadcasting from lane 0 lets it keep loop counters, ring stages and MMA descriptors
+  // in uniform registers (otherwise each tcgen05.mma is preceded by vector-to-uniform moves).
+  __device__ __forceinline__ void make_warp_uniform() {
+    head = __shfl_sync(0xffffffffu, head, 0);
+    batch = __shfl_sync(0xffffffffu, batch, 0);
+    kv_head = __shfl_sync(0xffffffffu, kv_head, 0);
+    q_row0 = __shfl_sync(0xffffffffu, q_row0, 0);
+    kv_len = __shfl_sync(0xffffffffu, kv_len, 0);
+    n0 = __shfl_sync(0xffffffffu, n0, 0);
+    n1 = __shfl_sync(0xffffffffu, n1, 0);
+    n_max = max(n0, n1);
+  }
+};
+
+// The kernel is persistent over the launch grid: every CTA starts on its own block index and, when a role has finished
+// an item, it reads the next block index the scheduler warp obtained through cluster launch control — the hardware
+// hands out the pending blocks in launch order (heavy-first, heads sharing K/V adjacent), there is no global counter.
+// Barrier phases, the KV ring and TMEM carry over from item to item, so the loads (Q, K, V) and the first Q K^T of
+// item i+1 overlap the last P V, the normalisation and the stores of item i.
 template <int D, typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-              const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, const Params p) {
+              const __grid_constant__ CUtensorMap tmap_v, const Params p) {
   using C = Cfg<D>;
   constexpr int NS = C::KV_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR_OFF);  // [2]
-  uint64_t* kv_full = q_full + 2;                                          // [NS]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR_OFF);  // [2]  TMA -> MMA
+  uint64_t* q_free = q_full + 2;                                           // [2]  softmax -> TMA: last Q_t K^T of the item retired
+  uint64_t* kv_full = q_free + 2;                                          // [NS]
   uint64_t* kv_empty = kv_full + NS;                                       // [NS]
   uint64_t* s_full = kv_empty + NS;                                        // [2]  MMA -> softmax
   uint64_t* p_half = s_full + 2;                                           // [2][2] softmax -> MMA: P columns [0,64) / [64,128) stored (one arrival per warp)
   uint64_t* pv_done = p_half + 4;                                          // [2]  MMA -> softmax (O_t updated)
-  uint64_t* s_free = pv_done + 2;                                          // [2]  softmax -> MMA: S_t has been read (decoupled pipeline)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* clc_full = pv_done + 2;                                        // [1]  launch-control response landed
+  uint64_t* clc_empty = clc_full + 1;                                      // [1]  all 10 reader warps have decoded it
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(clc_empty + 1);
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(tmem_ptr_smem + 4);       // 16 bytes, 16-byte aligned
+  constexpr int kClcReaders = 10;  // producer lane + MMA warp + 8 softmax warps
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
-
-  // heavy (late) query tiles first under a causal mask
-  const int pair = p.causal ? (p.num_pairs - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int kv_head = head / (p.Hq / p.Hkv);
-  const int q_row0 = pair * 2 * BLOCK_M;
-  int kv_len = p.Sk;
-  if (p.kv_lens != nullptr) kv_len = max(0, min(p.Sk, p.kv_lens[batch]));
-  const int n0 = num_kv_tiles(p, q_row0, kv_len);
-  const int n1 = num_kv_tiles(p, q_row0 + BLOCK_M, kv_len);
-  const int n_max = max(n0, n1);
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
-    tma_prefetch_desc(&tmap_o);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
+      mbar_init(&q_free[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_half[2 * i], 4);
       mbar_init(&p_half[2 * i + 1], 4);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 4);
     }
     for (int i = 0; i < NS; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
+    mbar_init(clc_full, 1);
+    mbar_init(clc_empty, kClcReaders);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -148,6 +177,29 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // Item k >= 1 of this CTA is launch-control response k-1. `whole_warp`: all 32 lanes of the calling warp read it.
+  auto next_work = [&](Work& w, int k, bool whole_warp) -> bool {
+    if (!p.persistent) return false;
+    mbar_wait_long(clc_full, static_cast<uint32_t>((k - 1) & 1));
+    int bx, by, bz;
+    bool ok = clc_query(clc_resp, bx, by, bz);
+    fence_proxy_async_smem();  // our generic-proxy read is ordered before the next async-proxy write of the response
+    if (whole_warp) {
+      __syncwarp();
+      ok = __shfl_sync(0xffffffffu, static_cast<int>(ok), 0) != 0;
+    }
+    if (lane == 0) mbar_arrive(clc_empty);
+    if (ok) {
+      w.set(p, bx, by, bz);
+      if (whole_warp) w.make_warp_uniform();
+    }
+    return ok;
+  };
+
+  Work w;
+  w.set(p, blockIdx.x, blockIdx.y, blockIdx.z);
+  if (warp_idx != 0) w.make_warp_uniform();  // (the producer runs on one lane)
+
   // register budget: 384 threads x 168 at launch; the producer warpgroup gives 96 per thread to the softmax
   // warpgroups (128 x 72 + 256 x 216 = 64512)
   if (warp_idx < 4) {
@@ -156,148 +208,138 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   if (warp_idx == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
-      for (int t = 0; t < 2; ++t) {
-        if (q_row0 + t * BLOCK_M < p.Sq) {
-          mbar_arrive_expect_tx(&q_full[t], C::TILE_BYTES);
-          uint8_t* sq = smem + C::SMEM_Q_OFF + t * C::TILE_BYTES;
-#pragma unroll
-          for (int c = 0; c < C::BOXES; ++c)
-            tma_load_4d(sq + c * 16384, &tmap_q, &q_full[t], c * 64, head, q_row0 + t * BLOCK_M, batch);
-        }
-      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < n_max; ++j) {
+      int q_loads[2] = {0, 0};
+      for (int k = 0;; ++k) {
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {  // 0: K(j), 1: V(j)
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&kv_full[stage], C::TILE_BYTES);
-          uint8_t* dst = smem + C::SMEM_KV_OFF + stage * C::TILE_BYTES;
-          const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
+        for (int t = 0; t < 2; ++t) {
+          if ((t == 0 ? w.n0 : w.n1) > 0) {
+            // the previous item's last Q_t K^T must have retired before its Q tile is overwritten
+            if (q_loads[t] > 0) mbar_wait(&q_free[t], static_cast<uint32_t>((q_loads[t] - 1) & 1));
+            ++q_loads[t];
+            mbar_arrive_expect_tx(&q_full[t], C::TILE_BYTES);
+            uint8_t* sq = smem + C::SMEM_Q_OFF + t * C::TILE_BYTES;
 #pragma unroll
-          for (int c = 0; c < C::BOXES; ++c)
-            tma_load_4d(dst + c * 16384, tm, &kv_full[stage], c * 64, kv_head, j * BLOCK_N, batch);
-          if (++stage == NS) { stage = 0; phase ^= 1; }
+            for (int c = 0; c < C::BOXES; ++c)
+              tma_load_4d(sq + c * 16384, &tmap_q, &q_full[t], c * 64, w.head, w.q_row0 + t * BLOCK_M, w.batch);
+          }
         }
+        for (int j = 0; j < w.n_max; ++j) {
+#pragma unroll
+          for (int kv = 0; kv < 2; ++kv) {  // 0: K(j), 1: V(j)
+            mbar_wait(&kv_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&kv_full[stage], C::TILE_BYTES);
+            uint8_t* dst = smem + C::SMEM_KV_OFF + stage * C::TILE_BYTES;
+            const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
+#pragma unroll
+            for (int c = 0; c < C::BOXES; ++c)
+              tma_load_4d(dst + c * 16384, tm, &kv_full[stage], c * 64, w.kv_head, j * BLOCK_N, w.batch);
+            if (++stage == NS) { stage = 0; phase ^= 1; }
+          }
+        }
+#ifdef FA_SINGLE_PRODUCER
+        break;
+#else
+        if (!next_work(w, k + 1, false)) break;
+#endif
       }
     }
   } else if (warp_idx == 1) {
     // ============================== MMA issuer ==============================
     // The whole warp runs the (warp-uniform) control flow so descriptors live in uniform registers; one elected
     // lane issues the tcgen05 instructions.
-    if (n_max > 0) {
-      constexpr uint32_t idesc_qk = make_idesc_f16(BLOCK_M, BLOCK_N, Pack2<T>::kIsBf16, false, false);
-      constexpr uint32_t idesc_pv = make_idesc_f16(BLOCK_M, D, Pack2<T>::kIsBf16, false, true);
-      const uint32_t sq_addr = smem_u32(smem + C::SMEM_Q_OFF);
-      const uint32_t skv_addr = smem_u32(smem + C::SMEM_KV_OFF);
-      // descriptor templates; the start-address field (bits 0-13, 16-byte units) is advanced by plain adds
-      const uint64_t qdesc0 = make_smem_desc_sw128(sq_addr, 16, 1024);
-      const uint64_t kdesc0 = make_smem_desc_sw128(skv_addr, 16, 1024);
-      const uint64_t vdesc0 = make_smem_desc_sw128(skv_addr, 16384, 1024);
-      constexpr uint32_t TILE16 = C::TILE_BYTES >> 4;
+    constexpr uint32_t idesc_qk = make_idesc_f16(BLOCK_M, BLOCK_N, Pack2<T>::kIsBf16, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_f16(BLOCK_M, D, Pack2<T>::kIsBf16, false, true);
+    const uint32_t sq_addr = smem_u32(smem + C::SMEM_Q_OFF);
+    const uint32_t skv_addr = smem_u32(smem + C::SMEM_KV_OFF);
+    // descriptor templates; the start-address field (bits 0-13, 16-byte units) is advanced by plain adds
+    const uint64_t qdesc0 = make_smem_desc_sw128(sq_addr, 16, 1024);
+    const uint64_t kdesc0 = make_smem_desc_sw128(skv_addr, 16, 1024);
+    const uint64_t vdesc0 = make_smem_desc_sw128(skv_addr, 16384, 1024);
+    constexpr uint32_t TILE16 = C::TILE_BYTES >> 4;
 
-      auto issue_qk = [&](int t, int k_stage) {
-        const uint64_t qd = qdesc0 + static_cast<uint64_t>(t * TILE16);
-        const uint64_t kd = kdesc0 + static_cast<uint64_t>(k_stage * TILE16);
-        const uint32_t d_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128);
-        if (elect_one()) {
+    // S_t = Q_t K^T
+    auto issue_qk = [&](int t, int k_stage) {
+      const uint64_t qd = qdesc0 + static_cast<uint64_t>(t * TILE16);
+      const uint64_t kd = kdesc0 + static_cast<uint64_t>(k_stage * TILE16);
+      const uint32_t d_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(t * 128);
+      if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;  // 16-byte units: next 64-col box / next 32 bytes
-            umma_ss(d_tmem, qd + off, kd + off, idesc_qk, ks > 0 ? 1u : 0u);
-          }
-          umma_commit(&s_full[t]);
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;  // 16-byte units: next 64-col box / next 32 bytes
+          umma_ss(d_tmem, qd + off, kd + off, idesc_qk, ks > 0 ? 1u : 0u);
         }
-        __syncwarp();
-      };
-      // P V for keys [64*part, 64*part+64) of the tile: issued as soon as that half of P is in TMEM, so the tensor
-      // pipe works on the first half while the softmax warps still exponentiate the second
-      auto issue_pv = [&](int t, int v_stage, int part, bool accumulate) {
-        const uint64_t vd = vdesc0 + static_cast<uint64_t>(v_stage * TILE16);
-        const uint32_t d_tmem = tmem_base + C::TMEM_O + static_cast<uint32_t>(t * D);
-        const uint32_t p_tmem = tmem_base + C::TMEM_P + static_cast<uint32_t>(t) * C::TMEM_P_STRIDE;
-        if (elect_one()) {
+        umma_commit(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    // P V for keys [64*part, 64*part+64) of the tile: issued as soon as that half of P is in TMEM, so the tensor
+    // pipe works on the first half while the softmax warps still exponentiate the second
+    auto issue_pv = [&](int t, int v_stage, int part, bool accumulate) {
+      const uint64_t vd = vdesc0 + static_cast<uint64_t>(v_stage * TILE16);
+      const uint32_t d_tmem = tmem_base + C::TMEM_O + static_cast<uint32_t>(t * D);
+      const uint32_t p_tmem = tmem_base + C::TMEM_P + static_cast<uint32_t>(t * 128);
+      if (elect_one()) {
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const int ks = part * 4 + k4;
-            umma_ts(d_tmem, p_tmem + ks * 8, vd + static_cast<uint64_t>(ks * 128), idesc_pv,
-                    (accumulate || ks > 0) ? 1u : 0u);
-          }
-          if (part == 1) umma_commit(&pv_done[t]);
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int ks = part * 4 + k4;
+          umma_ts(d_tmem, p_tmem + ks * 8, vd + static_cast<uint64_t>(ks * 128), idesc_pv,
+                  (accumulate || ks > 0) ? 1u : 0u);
         }
-        __syncwarp();
-      };
-      auto release = [&](int stage) {
-        if (elect_one()) umma_commit(&kv_empty[stage]);
-        __syncwarp();
-      };
+        if (part == 1) umma_commit(&pv_done[t]);
+      }
+      __syncwarp();
+    };
+    auto release = [&](int stage) {
+      if (elect_one()) umma_commit(&kv_empty[stage]);
+      __syncwarp();
+    };
 
-      if (n0 > 0) mbar_wait(&q_full[0], 0);
-      if (n1 > 0) mbar_wait(&q_full[1], 0);
-      // ring bookkeeping: item 2j = K(j), item 2j+1 = V(j); (stage, phase) advance by one per item
-      int k_stage = 0;          // stage of K(j+1) while in iteration j (K(0) before the loop)
-      uint32_t k_phase = 0;
-      mbar_wait(&kv_full[k_stage], k_phase);
-      tc_fence_after();
-      if (n0 > 0) issue_qk(0, k_stage);
-      if (n1 > 0) issue_qk(1, k_stage);
-      release(k_stage);  // K(0) is free once both S MMAs retire
+    // ring bookkeeping: the KV ring carries K(0),V(0),K(1),V(1),... of item after item; (stage, phase) advance by one
+    // per tile. k_stage = stage of the next K tile to consume.
+    int k_stage = 0;
+    uint32_t k_phase = 0;
+    uint32_t it_par[2] = {0, 0};  // parity of the KV iterations completed per query tile over all items
+    uint32_t q_par[2] = {0, 0};   // parity of the Q tiles consumed per query tile
+    for (int k = 0;; ++k) {
+      if (w.n_max > 0) {
+        const int nt[2] = {w.n0, w.n1};
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          if (nt[t] > 0) { mbar_wait(&q_full[t], q_par[t]); q_par[t] ^= 1; }
+        mbar_wait(&kv_full[k_stage], k_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          if (nt[t] > 0) issue_qk(t, k_stage);
+        release(k_stage);  // K(0) is free once both S MMAs retire
 
-      for (int j = 0; j < n_max; ++j) {
-        int v_stage = k_stage + 1;
-        uint32_t v_phase = k_phase;
-        if (v_stage == NS) { v_stage = 0; v_phase ^= 1; }
-        k_stage = v_stage + 1;
-        k_phase = v_phase;
-        if (k_stage == NS) { k_stage = 0; k_phase ^= 1; }
-        const bool has_next = (j + 1 < n_max);
-        if constexpr (C::DECOUPLED) {
-          // next Q K^T first: it only needs K(j+1) and the softmax warps to have READ S_t(j)
-          if (has_next) {
-            mbar_wait(&kv_full[k_stage], k_phase);
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int nt_t = t == 0 ? n0 : n1;
-              if (j + 1 < nt_t) {
-                mbar_wait(&s_free[t], static_cast<uint32_t>(j & 1));
-                tc_fence_after();
-                issue_qk(t, k_stage);
-              }
-            }
-            release(k_stage);
-          }
-          mbar_wait(&kv_full[v_stage], v_phase);
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int nt_t = t == 0 ? n0 : n1;
-            if (j < nt_t) {
-              mbar_wait(&p_half[2 * t], static_cast<uint32_t>(j & 1));
-              tc_fence_after();
-              issue_pv(t, v_stage, 0, j > 0);
-              mbar_wait(&p_half[2 * t + 1], static_cast<uint32_t>(j & 1));
-              tc_fence_after();
-              issue_pv(t, v_stage, 1, true);
-            }
-          }
-          release(v_stage);
-        } else {
+        for (int j = 0; j < w.n_max; ++j) {
+          int v_stage = k_stage + 1;
+          uint32_t v_phase = k_phase;
+          if (v_stage == NS) { v_stage = 0; v_phase ^= 1; }
+          k_stage = v_stage + 1;
+          k_phase = v_phase;
+          if (k_stage == NS) { k_stage = 0; k_phase ^= 1; }
+          const bool has_next = (j + 1 < w.n_max);
           mbar_wait(&kv_full[v_stage], v_phase);
           bool next_k_ready = false;
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const int nt_t = t == 0 ? n0 : n1;
-            if (j < nt_t) {
+            if (j < nt[t]) {
+              const uint32_t par = (it_par[t] + static_cast<uint32_t>(j)) & 1;
               if (lane == 0) FA_STAMP(2 + t, j, 0);
-              mbar_wait(&p_half[2 * t], static_cast<uint32_t>(j & 1));
+              mbar_wait(&p_half[2 * t], par);
               tc_fence_after();
               if (lane == 0) FA_STAMP(2 + t, j, 1);
               issue_pv(t, v_stage, 0, j > 0);
-              mbar_wait(&p_half[2 * t + 1], static_cast<uint32_t>(j & 1));
+              mbar_wait(&p_half[2 * t + 1], par);
               tc_fence_after();
               issue_pv(t, v_stage, 1, true);
               if (lane == 0) FA_STAMP(2 + t, j, 2);
             }
-            if (j + 1 < nt_t) {
+            if (j + 1 < nt[t]) {
               if (!next_k_ready) {
                 mbar_wait(&kv_full[k_stage], k_phase);
                 tc_fence_after();
@@ -313,6 +355,27 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             release(k_stage);
           }
         }
+        it_par[0] = (it_par[0] + static_cast<uint32_t>(w.n0)) & 1;
+        it_par[1] = (it_par[1] + static_cast<uint32_t>(w.n1)) & 1;
+      }
+#ifdef FA_SINGLE_MMA
+      break;
+#else
+      if (!next_work(w, k + 1, true)) break;
+#endif
+    }
+  } else if (warp_idx == 3) {
+    // ============================== work scheduler ==============================
+    // Request k asks for the block that becomes item k+1 of this CTA; it is issued once every reader has decoded
+    // response k-1 (= has started item k), so one item is prefetched and none is hoarded.
+    if (p.persistent && lane == 0) {
+      for (int k = 0;; ++k) {
+        if (k > 0) mbar_wait_long(clc_empty, static_cast<uint32_t>((k - 1) & 1));
+        mbar_arrive_expect_tx(clc_full, 16);
+        clc_try_cancel(clc_resp, clc_full);
+        mbar_wait_long(clc_full, static_cast<uint32_t>(k & 1));
+        int bx, by, bz;
+        if (!clc_query(clc_resp, bx, by, bz)) break;  // grid exhausted: a failed request must not be repeated
       }
     }
   } else if (warp_idx >= 4) {
@@ -322,169 +385,170 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const int quad = warp_idx & 3;               // TMEM lane quadrant
     const int row = quad * 32 + lane;            // row inside the tile
     const int wg_tid = threadIdx.x - 128 - t * 128;
-    const int tile_row0 = q_row0 + t * BLOCK_M;
-    const int q_row = tile_row0 + row;
-    const int nt = t == 0 ? n0 : n1;
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + C::TMEM_S + static_cast<uint32_t>(t * 128);
-    const uint32_t tP = tmem_base + lane_addr + C::TMEM_P + static_cast<uint32_t>(t) * C::TMEM_P_STRIDE;
+    const uint32_t tP = tmem_base + lane_addr + C::TMEM_P + static_cast<uint32_t>(t * 128);
     const uint32_t tO = tmem_base + lane_addr + C::TMEM_O + static_cast<uint32_t>(t * D);
-    uint8_t* sO = smem + C::SMEM_Q_OFF + t * C::TILE_BYTES;  // Q_t's smem is reused for the output tile
+    uint32_t iters = 0;  // KV iterations of this query tile over all items (barrier parities)
+    // barrier addresses of this warpgroup as one opaque base register + constant offsets (see smem_addr_opaque)
+    const uint32_t bar_base = smem_addr_opaque(q_full) + static_cast<uint32_t>(t) * 8u;
+    auto bar_off = [&](const uint64_t* b0) { return static_cast<uint32_t>((b0 - q_full) * 8); };
+    const uint32_t a_s_full = bar_base + bar_off(s_full);
+    const uint32_t a_pv_done = bar_base + bar_off(pv_done);
+    const uint32_t a_q_free = bar_base + bar_off(q_free);
+    const uint32_t a_p_half = bar_base + static_cast<uint32_t>(t) * 8u + bar_off(p_half);  // [2 * t + half]
 
-    float m_used = -INFINITY;  // reference max (log2 units) the stored P / O / l are relative to
-    float l_run = 0.f;
-    const int64_t q_pos_plus = static_cast<int64_t>(q_row) + p.causal_offset;  // last visible key under causal
+    for (int k = 0;; ++k) {
+      const int tile_row0 = w.q_row0 + t * BLOCK_M;
+      const int q_row = tile_row0 + row;
+      const int nt = t == 0 ? w.n0 : w.n1;
+      const int kv_len = w.kv_len;
+      float m_used = -INFINITY;  // reference max (log2 units) the stored P / O / l are relative to
+      float l_run = 0.f;
+      const int64_t q_pos_plus = static_cast<int64_t>(q_row) + p.causal_offset;  // last visible key under causal
 
-    for (int j = 0; j < nt; ++j) {
-      mbar_wait(&s_full[t], static_cast<uint32_t>(j & 1));
-      tc_fence_after();
-      if (wg_tid == 0) FA_STAMP(t, j, 0);
-      uint32_t s[128];
-      tmem_ld_x32(tS + 0, s + 0);
-      tmem_ld_x32(tS + 32, s + 32);
-      tmem_ld_x32(tS + 64, s + 64);
-      tmem_ld_x32(tS + 96, s + 96);
-      tmem_wait_ld();
-      if constexpr (C::DECOUPLED) {
-        // S_t is in registers: the MMA warp may overwrite it with Q_t K(j+1)^T while we do the softmax
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);
-      }
-      if (wg_tid == 0) FA_STAMP(t, j, 1);
-      // ---- masking: keys >= limit (relative to the tile) are invisible ----
-      const int kv0 = j * BLOCK_N;
-      int limit = kv_len - kv0;
-      if (p.causal) {
-        const int64_t cl = q_pos_plus - kv0 + 1;
-        if (cl < limit) limit = static_cast<int>(cl < 0 ? 0 : cl);
-      }
-      if (limit < BLOCK_N) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c >= limit) s[c] = 0xFF800000u;  // -inf
-      }
-      // ---- row max ----
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[c + 0]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
-      }
-      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
-      if (wg_tid == 0) FA_STAMP(t, j, 2);
-      // ---- lazy rescale decision ----
-      float alpha = 1.0f;
-      bool rescale = false;
-      if (j == 0) {
-        m_used = m_tile;
-      } else if (m_tile > m_used + kRescaleThreshold) {
-        alpha = fast_exp2(m_used - m_tile);  // m_used = -inf -> 0
-        m_used = m_tile;
-        l_run *= alpha;
-        rescale = true;
-      }
-      const bool any_rescale = __any_sync(0xffffffffu, rescale);
-      if (C::DECOUPLED && j > 0 && !any_rescale) {
-        // the separate P_t buffer may only be rewritten once P_t(j-1) V(j-1) has consumed it
-        mbar_wait(&pv_done[t], static_cast<uint32_t>((j - 1) & 1));
-      }
-      if (any_rescale) {
-        // O_t must contain P(j-1) V(j-1) before it is rescaled
-        mbar_wait(&pv_done[t], static_cast<uint32_t>((j - 1) & 1));
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t par = (iters + static_cast<uint32_t>(j)) & 1;
+        mbar_wait_addr(a_s_full, par);
         tc_fence_after();
+        // the commit behind s_full covers every earlier MMA: once the item's last S tile is visible, Q_t is free
+        if (j + 1 == nt && wg_tid == 0) mbar_arrive_addr(a_q_free);
+        if (wg_tid == 0) FA_STAMP(t, j, 0);
+        uint32_t s[128];
+        tmem_ld_x32(tS + 0, s + 0);
+        tmem_ld_x32(tS + 32, s + 32);
+        tmem_ld_x32(tS + 64, s + 64);
+        tmem_ld_x32(tS + 96, s + 96);
+        tmem_wait_ld();
+        if (wg_tid == 0) FA_STAMP(t, j, 1);
+        // ---- masking: keys >= limit (relative to the tile) are invisible ----
+        const int kv0 = j * BLOCK_N;
+        int limit = kv_len - kv0;
+        if (p.causal) {
+          const int64_t cl = q_pos_plus - kv0 + 1;
+          if (cl < limit) limit = static_cast<int>(cl < 0 ? 0 : cl);
+        }
+        if (limit < BLOCK_N) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= limit) s[c] = 0xFF800000u;  // -inf
+        }
+        // ---- row max ----
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[c + 0]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+        }
+        const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+        if (wg_tid == 0) FA_STAMP(t, j, 2);
+        // ---- lazy rescale decision ----
+        float alpha = 1.0f;
+        bool rescale = false;
+        if (j == 0) {
+          m_used = m_tile;
+        } else if (m_tile > m_used + kRescaleThreshold) {
+          alpha = fast_exp2(m_used - m_tile);  // m_used = -inf -> 0
+          m_used = m_tile;
+          l_run *= alpha;
+          rescale = true;
+        }
+        if (__any_sync(0xffffffffu, rescale)) {
+          // O_t must contain P(j-1) V(j-1) before it is rescaled
+          mbar_wait_addr(a_pv_done, par ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_x32(tO + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tO + c * 32, o);
+          }
+        }
+        // ---- P = exp2(s * scale - m_used), row sum, pack to 16 bit, store to TMEM (two halves of 64 keys) ----
+        const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        const float2 nm2 = make_float2(-m_ref, -m_ref);
+        float2 sum2 = make_float2(0.f, 0.f);
+        uint32_t pk0[32], pk1[32];
+        // columns c, c+1: packed fp32x2 FMA / ADD halve the issue slots of the scale-subtract and the row sum
+        auto exp_pair = [&](int c) -> uint32_t {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
+          const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          sum2 = __fadd2_rn(sum2, e);
+          return Pack2<T>::pack(e.x, e.y);
+        };
+        auto publish = [&](int half) {
+          tmem_wait_st();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_addr(a_p_half + static_cast<uint32_t>(half) * 8u);
+        };
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+        tmem_st_x32(tP, pk0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i);
+        publish(0);  // the first half of P has landed by now: its P V MMAs start while we finish the row
+#pragma unroll
+        for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i);
+        tmem_st_x32(tP + 32, pk1);
+        l_run += sum2.x + sum2.y;
+        if (wg_tid == 0) FA_STAMP(t, j, 6);
+        publish(1);
+        if (wg_tid == 0) FA_STAMP(t, j, 7);
+      }
+
+      // ---- epilogue: O / l -> 16 bit -> global (each thread owns one 2*D-byte output row); LSE -> global ----
+      // No shared-memory staging: the Q buffers stay free for the next item's loads, and O_t is back in registers
+      // before this warp publishes the next item's first P (which is what lets the MMA warp overwrite O_t).
+      if (tile_row0 < p.Sq) {
+        float inv_l = 0.f;
+        float lse_val = -INFINITY;
+        if (nt > 0) {
+          mbar_wait_addr(a_pv_done, (iters + static_cast<uint32_t>(nt - 1)) & 1);
+          tc_fence_after();
+          if (l_run > 0.f) {
+            inv_l = 1.0f / l_run;
+            lse_val = (m_used + log2f(l_run)) * kLn2;
+          }
+        }
+        const bool row_ok = q_row < p.Sq;
+        if (p.lse != nullptr && row_ok) p.lse[(static_cast<int64_t>(w.batch) * p.Hq + w.head) * p.Sq + q_row] = lse_val;
+        T* orow = reinterpret_cast<T*>(p.o) + static_cast<int64_t>(w.batch) * p.o_sb + static_cast<int64_t>(q_row) * p.o_ss +
+                  static_cast<int64_t>(w.head) * p.o_sh;
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
           uint32_t o[32];
-          tmem_ld_x32(tO + c * 32, o);
-          tmem_wait_ld();
+          if (nt > 0) {
+            tmem_ld_x32(tO + c * 32, o);
+            tmem_wait_ld();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x32(tO + c * 32, o);
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 pk;
+              pk.x = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
+              pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
+              pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
+              pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
+            }
+          }
         }
       }
-      // ---- P = exp2(s * scale - m_used), row sum, pack to 16 bit, store to TMEM (two halves of 64 keys) ----
-      const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      const float2 nm2 = make_float2(-m_ref, -m_ref);
-      float2 sum2 = make_float2(0.f, 0.f);
-      uint32_t pk0[32], pk1[32];
-      // columns c, c+1: packed fp32x2 FMA / ADD halve the issue slots of the scale-subtract and the row sum
-      auto exp_pair = [&](int c) -> uint32_t {
-        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
-        const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-        sum2 = __fadd2_rn(sum2, e);
-        return Pack2<T>::pack(e.x, e.y);
-      };
-      auto publish = [&](int half) {
-        tmem_wait_st();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_half[2 * t + half]);
-      };
-#pragma unroll
-      for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
-      tmem_st_x32(tP, pk0);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i);
-      publish(0);  // the first half of P has landed by now: its P V MMAs start while we finish the row
-#pragma unroll
-      for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i);
-      tmem_st_x32(tP + 32, pk1);
-      l_run += sum2.x + sum2.y;
-      if (wg_tid == 0) FA_STAMP(t, j, 6);
-      publish(1);
-      if (wg_tid == 0) FA_STAMP(t, j, 7);
-    }
-
-    // ---- epilogue: O / l -> 16 bit -> smem (128B swizzle) -> TMA store; LSE -> global ----
-    if (tile_row0 < p.Sq) {
-      float inv_l = 0.f;
-      float lse_val = -INFINITY;
-      if (nt > 0) {
-        mbar_wait(&pv_done[t], static_cast<uint32_t>((nt - 1) & 1));
-        tc_fence_after();
-        if (l_run > 0.f) {
-          inv_l = 1.0f / l_run;
-          lse_val = (m_used + log2f(l_run)) * kLn2;
-        }
-      } else {
-        mbar_wait(&q_full[t], 0);  // the Q tile load into this buffer must have landed before we overwrite it
-      }
-      if (p.lse != nullptr && q_row < p.Sq)
-        p.lse[(static_cast<int64_t>(batch) * p.Hq + head) * p.Sq + q_row] = lse_val;
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t o[32];
-        if (nt > 0) {
-          tmem_ld_x32(tO + c * 32, o);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = 0u;
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 pk;
-          pk.x = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
-          pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
-          pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
-          pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
-          const int col = c * 32 + q4 * 8;       // first column of this 16-byte chunk
-          const int box = col >> 6;
-          const int c16 = (col & 63) >> 3;
-          *reinterpret_cast<uint4*>(sO + box * 16384 + row * 128 + ((c16 ^ (row & 7)) << 4)) = pk;
-        }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2 + t, 128);
-      if (wg_tid == 0) {
-#pragma unroll
-        for (int c = 0; c < C::BOXES; ++c) tma_store_4d(&tmap_o, sO + c * 16384, c * 64, head, tile_row0, batch);
-        tma_store_commit();
-        tma_store_wait_all<0>();
-      }
+      iters += static_cast<uint32_t>(nt);
+#ifdef FA_SINGLE_SOFTMAX
+      break;
+#else
+      if (!next_work(w, k + 1, true)) break;
+#endif
     }
   }
 
@@ -497,8 +561,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 }
 
 template <int D, typename T>
-int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, const Params& p,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t stream) {
   auto kern = fa_fwd_kernel<D, T>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -506,7 +569,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
     attr_set = true;
   }
   dim3 grid(p.num_pairs, p.Hq, p.B);
-  kern<<<grid, NUM_THREADS, Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, to, p);
+  kern<<<grid, NUM_THREADS, Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }
@@ -548,13 +611,21 @@ extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o,
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "fa_fwd: dtype must be bf16 or fp16");
   B200_CHECK_ARG(softmax_scale > 0.f, "fa_fwd: softmax_scale must be positive");
   B200_CHECK_ARG(B <= 65535 && Hq <= 65535, "fa_fwd: B and Hq must be <= 65535");
-  CUtensorMap tq, tk, tv, to;
+  CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = fa::make_bshd_tmap(&tq, q, B, Sq, Hq, D, q_strides, "q"))) return rc;
   if ((rc = fa::make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
   if ((rc = fa::make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
-  if ((rc = fa::make_bshd_tmap(&to, o, B, Sq, Hq, D, o_strides, "o"))) return rc;
+  for (int i = 0; i < 3; ++i)
+    B200_CHECK_ARG(o_strides[i] > 0 && o_strides[i] % 8 == 0, "fa_fwd: o stride %d = %lld must be a positive multiple of 8 elements",
+                   i, (long long)o_strides[i]);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "fa_fwd: o must be 16-byte aligned");
   fa::Params p;
+  p.o = o;
+  p.o_sb = o_strides[0]; p.o_ss = o_strides[1]; p.o_sh = o_strides[2];
+  // B200_FA_PERSISTENT=0 in the environment: every CTA handles only its own block (no work stealing)
+  static const bool persistent = [] { const char* e = getenv("B200_FA_PERSISTENT"); return !(e && e[0] == '0'); }();
+  p.persistent = persistent ? 1 : 0;
   p.lse = lse;
   p.kv_lens = kv_lens;
   p.B = B; p.Sq = Sq; p.Sk = Sk; p.Hq = Hq; p.Hkv = Hkv;
@@ -564,9 +635,9 @@ extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o,
   p.num_pairs = (Sq + 2 * fa::BLOCK_M - 1) / (2 * fa::BLOCK_M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (D == 128) {
-    return dtype == B200_DTYPE_BF16 ? fa::launch<128, __nv_bfloat16>(tq, tk, tv, to, p, s)
-                                    : fa::launch<128, __half>(tq, tk, tv, to, p, s);
+    return dtype == B200_DTYPE_BF16 ? fa::launch<128, __nv_bfloat16>(tq, tk, tv, p, s)
+                                    : fa::launch<128, __half>(tq, tk, tv, p, s);
   }
-  return dtype == B200_DTYPE_BF16 ? fa::launch<64, __nv_bfloat16>(tq, tk, tv, to, p, s)
-                                  : fa::launch<64, __half>(tq, tk, tv, to, p, s);
+  return dtype == B200_DTYPE_BF16 ? fa::launch<64, __nv_bfloat16>(tq, tk, tv, p, s)
+                                  : fa::launch<64, __half>(tq, tk, tv, p, s);
 }
