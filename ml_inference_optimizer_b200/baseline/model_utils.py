@@ -27,7 +27,10 @@ def add_paged_attention_to_model(model: nn.Module, config: Optional[_fa.FlashAtt
     warning and returns the model untouched, which hides a silently unoptimised model."""
     model = deepcopy(model)
     if not any(isinstance(m, _fa._HFAttentionAdapter) for m in model.modules()):
-        causal_cfg = config or _fa.FlashAttentionConfig(causal=True)
+        # compute in the model's own 16-bit dtype so the paged cache (allocated in that dtype) matches q
+        dtype = next(model.parameters()).dtype
+        prec = {torch.bfloat16: "bf16", torch.float16: "fp16"}.get(dtype, "bf16")
+        causal_cfg = config or _fa.FlashAttentionConfig(causal=True, precision=prec)
         model = _fa.ModelConverter(causal_cfg).convert_model(model)
     if not any(isinstance(m, _fa._HFAttentionAdapter) for m in model.modules()):
         raise ValueError("add_paged_attention_to_model: no convertible attention layer found in the model")

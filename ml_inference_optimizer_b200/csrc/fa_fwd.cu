@@ -4,17 +4,21 @@
 // (kernels/triton/flash_attention_kernels.py:38-325, :1150-1358) and, per ring step,
 // triton_ring_attention_forward (kernels/triton/attention_kernels.py:909-998).
 //
-// One CTA owns two 128-row query tiles of one (batch, head) and walks the KV sequence in 128-key tiles:
-//   warp 0      TMA producer   : Q tiles once, then K(j), V(j) through an mbarrier ring (128-byte swizzle)
+// One work item = two 128-row query tiles of one (batch, head), walked over the KV sequence in 128-key tiles:
+//   warp 0      TMA producer   : Q tiles, then K(j), V(j) through an mbarrier ring (128-byte swizzle)
 //   warp 1      MMA issuer     : S_t = Q_t K^T  (tcgen05.mma SS, 128x128xD, fp32 accumulators in TMEM)
 //                                O_t += P_t V   (tcgen05.mma TS: P read from TMEM, V MN-major from smem)
 //   warp 2      TMEM allocator : 512 columns = [S0 | S1 | O0 | O1]; P_t (16-bit) overlays the upper half of S_t
+//   warp 3      work scheduler : cluster launch control — asks the hardware for the block index of a CTA of this
+//                                grid that has not started yet; the CTA then processes that block as well
 //   warps 4-7   softmax of tile 0, warps 8-11 softmax of tile 1: one thread per query row — tcgen05.ld the
 //               row of S, running max / sum in fp32 registers (no shuffles), exp2 with the scale folded in,
 //               P written back to TMEM with tcgen05.st, lazy O rescale (only when the row max grew by > 2^8),
-//               final O / l -> 16-bit -> swizzled smem -> TMA store, LSE -> global.
+//               final O / l -> 16-bit -> global (one 2*D-byte row per thread), LSE -> global.
 // The two query tiles ping-pong: while the softmax warps of tile 0 work on S_0(j+1), the tensor core runs
-// P_1(j) V(j) and Q_1 K(j+1)^T. Causal tiles above the diagonal are never loaded or computed.
+// P_1(j) V(j) and Q_1 K(j+1)^T. Causal tiles above the diagonal are never loaded or computed. CTAs are persistent
+// over the launch grid: barrier phases, the KV ring and TMEM carry over from item to item, so the loads and the first
+// Q K^T of the next item overlap the tail of the current one.
 
 #include "common.cuh"
 #include "host_common.h"
