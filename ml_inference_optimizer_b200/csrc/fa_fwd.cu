@@ -437,6 +437,35 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           for (int c = 0; c < 128; ++c)
             if (c >= limit) s[c] = 0xFF800000u;  // -inf
         }
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        float2 nm2, sum2;
+        uint32_t pk0[32], pk1[32];
+        // columns c, c+1: packed fp32x2 FMA / ADD halve the issue slots of the scale-subtract and the row sum
+        auto exp_pair = [&](int c) -> uint32_t {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
+          const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          sum2 = __fadd2_rn(sum2, e);
+          return Pack2<T>::pack(e.x, e.y);
+        };
+        auto set_reference = [&]() {
+          const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
+          nm2 = make_float2(-m_ref, -m_ref);
+          sum2 = make_float2(0.f, 0.f);
+        };
+        auto publish = [&](int half) {
+          tmem_wait_st();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_addr(a_p_half + static_cast<uint32_t>(half) * 8u);
+        };
+        // ---- speculative first half: P = exp2(s * scale - m_used) against the reference max of the PREVIOUS tiles ----
+        // With lazy rescaling the reference only changes when the row max grows by more than 2^8, which is rare after
+        // the first tiles, so the exponentials (MUFU pipe) need not wait for this tile's row max (ALU pipe): both run
+        // concurrently and the max leaves the critical path. If the reference does change (always for the first tile of
+        // an item) the first half is recomputed. (Skipping the speculation for j == 0 instead was measured: the second
+        // conditional copy of the exponentials makes ptxas spill in this loop, +40 % cycles.)
+        set_reference();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
         // ---- row max ----
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -451,48 +480,33 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         // ---- lazy rescale decision ----
         float alpha = 1.0f;
         bool rescale = false;
-        if (j == 0) {
-          m_used = m_tile;
-        } else if (m_tile > m_used + kRescaleThreshold) {
-          alpha = fast_exp2(m_used - m_tile);  // m_used = -inf -> 0
+        if (m_tile > m_used + kRescaleThreshold) {  // (m_used = -inf until the first visible key)
+          alpha = fast_exp2(m_used - m_tile);       // m_used = -inf -> 0
           m_used = m_tile;
           l_run *= alpha;
           rescale = true;
         }
         if (__any_sync(0xffffffffu, rescale)) {
-          // O_t must contain P(j-1) V(j-1) before it is rescaled
-          mbar_wait_addr(a_pv_done, par ^ 1);
-          tc_fence_after();
+          if (j > 0) {
+            // O_t must contain P(j-1) V(j-1) before it is rescaled
+            mbar_wait_addr(a_pv_done, par ^ 1);
+            tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_x32(tO + c * 32, o);
-            tmem_wait_ld();
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld_x32(tO + c * 32, o);
+              tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_x32(tO + c * 32, o);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_x32(tO + c * 32, o);
+            }
           }
-        }
-        // ---- P = exp2(s * scale - m_used), row sum, pack to 16 bit, store to TMEM (two halves of 64 keys) ----
-        const float m_ref = (m_used == -INFINITY) ? 0.f : m_used;
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-        const float2 nm2 = make_float2(-m_ref, -m_ref);
-        float2 sum2 = make_float2(0.f, 0.f);
-        uint32_t pk0[32], pk1[32];
-        // columns c, c+1: packed fp32x2 FMA / ADD halve the issue slots of the scale-subtract and the row sum
-        auto exp_pair = [&](int c) -> uint32_t {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
-          const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
-          sum2 = __fadd2_rn(sum2, e);
-          return Pack2<T>::pack(e.x, e.y);
-        };
-        auto publish = [&](int half) {
-          tmem_wait_st();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_addr(a_p_half + static_cast<uint32_t>(half) * 8u);
-        };
+          // the speculation failed for at least one row of this warp: redo the first half against the new reference
+          set_reference();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+          for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+        }
+        // ---- store P (16 bit) to TMEM in two halves of 64 keys; second half of the exponentials ----
         tmem_st_x32(tP, pk0);
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i);
