@@ -509,6 +509,25 @@ __device__ __forceinline__ float fast_exp2_ordered(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair of values on the FMA pipe (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic minimax
+// polynomial for 2^f (max relative error 7.7e-5, far below the 16-bit rounding of the result's consumer), exponent
+// inserted with an integer shift-add. x is clamped at -125, so -inf maps to 2^-125 (~2e-38), not to an exact zero.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 n = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.05508868396282196f, 0.05508868396282196f),
+                        make_float2(0.24260404706001282f, 0.24260404706001282f));
+  p = __ffma2_rn(p, f, make_float2(0.6932762265205383f, 0.6932762265205383f));
+  p = __ffma2_rn(p, f, make_float2(0.9999289512634277f, 0.9999289512634277f));
+  float2 e;
+  e.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  e.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return e;
+}
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

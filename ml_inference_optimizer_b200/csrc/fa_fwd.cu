@@ -441,9 +441,15 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float2 nm2, sum2;
         uint32_t pk0[32], pk1[32];
         // columns c, c+1: packed fp32x2 FMA / ADD halve the issue slots of the scale-subtract and the row sum
+#ifndef B200_FA_POLY_MOD
+#define B200_FA_POLY_MOD 4
+#endif
+        // One pair in B200_FA_POLY_MOD takes the exponential on the FMA pipe (exp2_poly2) instead of the MUFU pipe,
+        // which is the busier of the two in this loop (0 = MUFU only).
         auto exp_pair = [&](int c) -> uint32_t {
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
-          const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          const bool poly = B200_FA_POLY_MOD > 0 && ((c >> 1) % (B200_FA_POLY_MOD > 0 ? B200_FA_POLY_MOD : 1)) == 1;
+          const float2 e = poly ? exp2_poly2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
           sum2 = __fadd2_rn(sum2, e);
           return Pack2<T>::pack(e.x, e.y);
         };
@@ -529,7 +535,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         if (nt > 0) {
           mbar_wait_addr(a_pv_done, (iters + static_cast<uint32_t>(nt - 1)) & 1);
           tc_fence_after();
-          if (l_run > 0.f) {
+          if (l_run > 0.f && m_used != -INFINITY) {  // (a row without a visible key keeps m_used = -inf)
             inv_l = 1.0f / l_run;
             lse_val = (m_used + log2f(l_run)) * kLn2;
           }

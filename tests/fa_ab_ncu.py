@@ -35,6 +35,8 @@ for n in names:
 
 torch.manual_seed(0)
 B, H, D, S = 4, 32, 128, 8192
+if os.environ.get("FA_AB_D") == "64":
+    B, H, D, S = 8, 12, 64, 8192   # GPT-2 head shape, longer sequence so the fit has the same tile counts
 q = torch.randn(B, S, H, D, device="cuda", dtype=torch.bfloat16)
 k = torch.randn_like(q); v = torch.randn_like(q); o = torch.empty_like(q)
 ev = lambda: torch.cuda.Event(enable_timing=True)

@@ -20,6 +20,7 @@ for pid, name in zip(pids, names):
 for c in cases[1:9]:
     print(f"{c:8s}", ' | '.join(f"{n}: " + ','.join(f"{cy/1e3:.0f}" for cy in tab[c][n]) + " kcyc" for n in names))
 for n in names:
-    waves = 4096 / 148
+    import os
+    waves = (8 * 12 * 32 if os.environ.get('FA_AB_D') == '64' else 4096) / 148
     slope = (tab['full'][n][0] - tab['sk4096'][n][0]) / 32 / waves
     print(f"{n}: {slope:.0f} cycles per KV iteration (2 query tiles), fixed {tab['sk128'][n][0]/waves - slope:.0f} cycles per item")
