@@ -387,57 +387,6 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       : "memory");
 }
 
-// Predicated forms: executed by the whole (converged) warp, the instruction itself is guarded by `issue` (true in
-// one elected lane). Without a divergent branch around the issue code the compiler keeps the descriptor arithmetic
-// in the uniform datapath instead of computing it per lane and moving it over with R2UR right before every MMA.
-__device__ __forceinline__ uint32_t elect_one_u32() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(pred));
-  return pred;
-}
-__device__ __forceinline__ void umma_ss_if(uint32_t issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n"
-      :
-      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_ts_if(uint32_t issue, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n"
-      :
-      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_if(uint32_t issue, uint64_t* bar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(issue)
-      : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // TMEM <-> registers. Shape 32x32b: thread i of the warp owns TMEM lane (32*(warp%4) + i) and receives
 // N consecutive 32-bit columns.
@@ -453,12 +402,6 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* r) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-}
-
-__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
 }
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* r) {
@@ -500,13 +443,6 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// Same instruction, but pinned in program order relative to other volatile asm (tcgen05.ld/st, mbarrier ops): used
-// where the position of the exponentials relative to a TMEM store is part of the pipeline design.
-__device__ __forceinline__ float fast_exp2_ordered(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 // 2^x for a pair of values on the FMA pipe (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic minimax

@@ -55,10 +55,7 @@ struct Cfg {
   // behind P_t(j) V(j) on the tensor pipe. (Separate P buffers for D = 64 were measured slower: both tiles then run
   // in lockstep and share the MUFU pipe, 606 vs 701 TFLOP/s.)
   static constexpr uint32_t TMEM_S = 0;    // + t * 128
-#ifndef B200_FA_TMEM_P
-#define B200_FA_TMEM_P 64
-#endif
-  static constexpr uint32_t TMEM_P = B200_FA_TMEM_P;  // + t * 128
+  static constexpr uint32_t TMEM_P = 64;   // + t * 128
   static constexpr uint32_t TMEM_O = 256;  // + t * D
 };
 
@@ -242,11 +239,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
-#ifdef FA_SINGLE_PRODUCER
-        break;
-#else
         if (!next_work(w, k + 1, false)) break;
-#endif
       }
     }
   } else if (warp_idx == 1) {
@@ -362,11 +355,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         it_par[0] = (it_par[0] + static_cast<uint32_t>(w.n0)) & 1;
         it_par[1] = (it_par[1] + static_cast<uint32_t>(w.n1)) & 1;
       }
-#ifdef FA_SINGLE_MMA
-      break;
-#else
       if (!next_work(w, k + 1, true)) break;
-#endif
     }
   } else if (warp_idx == 3) {
     // ============================== work scheduler ==============================
@@ -568,11 +557,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
       iters += static_cast<uint32_t>(nt);
-#ifdef FA_SINGLE_SOFTMAX
-      break;
-#else
       if (!next_work(w, k + 1, true)) break;
-#endif
     }
   }
 
