@@ -83,6 +83,26 @@ def test_fa_fwd_vs_oracle(ops, B, Sq, Sk, Hq, Hkv, D, causal, offset, kv_lens):
     check_lse(lse, rl)
 
 
+@pytest.mark.parametrize("B,S,H,Hkv,D,causal,kv_lens", [
+    (6, 256, 64, 64, 64, True, None),                     # 384 one/two-iteration items: > 2 per SM, every CTA steals blocks
+    (3, 768, 80, 16, 128, True, None),                    # 720 items, GQA 5:1, mixed item lengths (heavy-first order)
+    (5, 512, 40, 40, 128, False, [512, 0, 37, 300, 1]),   # items with no key at all between normal ones
+])
+def test_fa_fwd_work_stealing_many_items(ops, B, S, H, Hkv, D, causal, kv_lens):
+    """The kernel is persistent: a CTA that finished its block takes over blocks that have not started (cluster launch
+    control), carrying barrier phases, the KV ring and TMEM from item to item. Grids with several items per SM, item
+    lengths that differ by up to 6x and empty items exercise every carry-over; results must match the oracle exactly as
+    for a single item per CTA."""
+    q, k, v = rand_qkv(B, S, S, H, Hkv, D, seed=11)
+    lens = None if kv_lens is None else torch.tensor(kv_lens, device="cuda", dtype=torch.int32)
+    o, lse = ops.flash_attn_fwd(q, k, v, causal=causal, kv_lens=lens, return_lse=True)
+    o2, lse2 = ops.flash_attn_fwd(q, k, v, causal=causal, kv_lens=lens, return_lse=True)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2), "result depends on which CTA picked up which block"
+    ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=causal, kv_lens=None if lens is None else lens.cpu())
+    check_out(o, ro)
+    check_lse(lse, rl)
+
+
 def test_fa_fwd_fp16(ops):
     q, k, v = rand_qkv(1, 512, 512, 2, 2, 128, dtype=torch.float16)
     o, lse = ops.flash_attn_fwd(q, k, v, causal=True, return_lse=True)
