@@ -334,7 +334,7 @@ def run_ours(args, w):
                          "ms_per_launch": gemm1_ms, "flops_per_launch": gemm1_flops,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_gemm1_v0_ncu.txt)
                          "traffic": 3.872766e9 if args.workload == "c3" else None,
-                         "other_kernels_ms": {"fa_fwd_kernel": attn_ms, "gemm_act_kernel<none> (down projection)": gemm2_ms}},
+                         "other_kernels_ms": {"fa_fwd_kernel": attn_ms, "gemm_act_pair_kernel<NONE> (down projection)": gemm2_ms}},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
                     "pipeline": "3 streams (H2D / kernels / D2H), double-buffered device tensors, pinned host buffers"},
