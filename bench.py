@@ -327,7 +327,7 @@ def run_ours(args, w):
             "config": {"workload": w["name"], "parallelism": f"dp{world} (independent batches per GPU, no collective)",
                        "l2": "inputs (q,k,v,x = %.0f MB per step) exceed the 126 MB L2" % (h2d / 1e6),
                        "attn_flops_per_step": fa, "mlp_flops_per_step": fm},
-            "roofline": {"kernel": "gemm_act_kernel<%s> (FusedMLP up%s GEMM with the activation fused in the epilogue)" %
+            "roofline": {"kernel": "gemm_act_pair_kernel<%s> (FusedMLP up%s GEMM on CTA pairs, activation fused in the epilogue)" %
                                    (act, "+gate" if act == "swiglu" else ""),
                          "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}): kernel timed inside a long step",
