@@ -461,6 +461,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         set_reference();
 #pragma unroll
         for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+        if (wg_tid == 0) FA_STAMP(t, j, 3);
         // ---- row max ----
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
@@ -506,6 +507,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i);
         publish(0);  // the first half of P has landed by now: its P V MMAs start while we finish the row
+        if (wg_tid == 0) FA_STAMP(t, j, 4);
 #pragma unroll
         for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i);
         tmem_st_x32(tP + 32, pk1);

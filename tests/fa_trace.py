@@ -23,7 +23,7 @@ torch.cuda.synchronize()
 t = buf.cpu().view(4, 64, 8)
 base = t[t > 0].min().item()
 names = {0: "softmax0", 1: "softmax1", 2: "mma(t=0)", 3: "mma(t=1)"}
-lab_s = ["s_ready", "ld_done", "max_done", "-", "-", "-", "exp+st", "published"]
+lab_s = ["s_ready", "ld_done", "max_done", "half0_exp", "pub0", "-", "exp+st", "published"]
 lab_m = ["wait_p", "p_ready", "pv_issued", "qk_issued"]
 for slot in range(4):
     print("==", names[slot], lab_s if slot < 2 else lab_m)
@@ -34,7 +34,7 @@ for slot in range(4):
 for slot in (0, 1):
     d = (t[slot, 9:40, 0] - t[slot, 8:39, 0]).float()
     print(names[slot], "period mean", d.mean().item(), "min", d.min().item(), "max", d.max().item())
-    for a, b in ((0, 1), (1, 2), (2, 6), (6, 7)):
+    for a, b in ((0, 1), (1, 3), (3, 2), (2, 4), (4, 6), (6, 7)):
         print(f"   {lab_s[a]:10s} -> {lab_s[b]:10s} {(t[slot, 8:40, b] - t[slot, 8:40, a]).float().mean().item():8.1f}")
     print(f"   pub1_done -> next s_ready {(t[slot, 9:40, 0] - t[slot, 8:39, 7]).float().mean().item():8.1f}")
 for slot in (2, 3):
