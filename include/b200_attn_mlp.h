@@ -85,6 +85,22 @@ int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 const int64_t o_strides[3], float softmax_scale, int causal, int64_t causal_offset,
                 const int32_t* kv_lens, int dtype, void* stream);
 
+/* ---- K1 in accumulate mode: one ring step --------------------------------------------------------------
+ * Same computation as b200_fa_fwd, but the result of this key block is merged in the kernel epilogue into a running
+ * fp32 output + LSE (the step of SequenceParallelAttention._ring_attention, parallelism/sequence_parallel.py:519-585,
+ * rebuilt exact with the merge algebra of kernels/triton/attention_kernels.py:1567-1585):
+ *   init != 0 : o_acc = O, lse_acc = LSE                       (first step)
+ *   init == 0 : lse = logaddexp(lse_acc, LSE); o_acc = o_acc*exp(lse_acc-lse) + O*exp(LSE-lse); lse_acc = lse
+ * Rows for which this block has no visible key leave the accumulator untouched (init: O = 0, LSE = -inf).
+ *   o_acc  : fp32, addressed by element strides acc_strides = (batch, seq, head), head dim contiguous, 16-byte aligned
+ *   lse_acc: fp32, rows of Sq contiguous, element strides lse_strides = (batch, head)
+ * No 16-bit output tensor and no separate merge pass: b200_cast_out converts the accumulator at the end.   */
+int b200_fa_fwd_accum(const void* q, const void* k, const void* v, float* o_acc, float* lse_acc, int B, int Sq, int Sk,
+                      int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                      const int64_t v_strides[3], const int64_t acc_strides[3], const int64_t lse_strides[2],
+                      float softmax_scale, int causal, int64_t causal_offset, const int32_t* kv_lens, int init, int dtype,
+                      void* stream);
+
 /* ---- LSE merge: combine two partial attention results over disjoint key sets ---------------------------
  * The online-softmax merge algebra of kernels/triton/attention_kernels.py:1567-1585, used by the ring
  * (parallelism/sequence_parallel.py:519-585 rebuilt exact):

@@ -70,6 +70,12 @@ struct Params {
   int64_t causal_offset;    // key j visible to query i iff j <= i + causal_offset
   int num_pairs;            // ceil(Sq / 256)
   int persistent;           // 1: a CTA that finished its block steals further blocks (cluster launch control)
+  // accumulate mode (ring steps): the result is merged into a running fp32 output + LSE instead of being written as 16 bit
+  float* o_acc;             // fp32, element strides (batch, seq, head) in acc_s*, head dim contiguous
+  int64_t acc_sb, acc_ss, acc_sh;
+  float* lse_acc;           // fp32, rows contiguous, element strides (batch, head)
+  int64_t lse_sb, lse_sh;
+  int acc_init;             // 1: overwrite the accumulator (first ring step), 0: log-sum-exp merge into it
 };
 
 // number of KV tiles a query tile [row0, row0+128) needs
@@ -121,7 +127,7 @@ struct Work {
 // hands out the pending blocks in launch order (heavy-first, heads sharing K/V adjacent), there is no global counter.
 // Barrier phases, the KV ring and TMEM carry over from item to item, so the loads (Q, K, V) and the first Q K^T of
 // item i+1 overlap the last P V, the normalisation and the stores of item i.
-template <int D, typename T>
+template <int D, typename T, bool ACCUM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
               const __grid_constant__ CUtensorMap tmap_v, const Params p) {
@@ -532,28 +538,81 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           }
         }
         const bool row_ok = q_row < p.Sq;
-        if (p.lse != nullptr && row_ok) p.lse[(static_cast<int64_t>(w.batch) * p.Hq + w.head) * p.Sq + q_row] = lse_val;
-        T* orow = reinterpret_cast<T*>(p.o) + static_cast<int64_t>(w.batch) * p.o_sb + static_cast<int64_t>(q_row) * p.o_ss +
-                  static_cast<int64_t>(w.head) * p.o_sh;
+        if constexpr (!ACCUM) {
+          if (p.lse != nullptr && row_ok) p.lse[(static_cast<int64_t>(w.batch) * p.Hq + w.head) * p.Sq + q_row] = lse_val;
+          T* orow = reinterpret_cast<T*>(p.o) + static_cast<int64_t>(w.batch) * p.o_sb + static_cast<int64_t>(q_row) * p.o_ss +
+                    static_cast<int64_t>(w.head) * p.o_sh;
 #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          if (nt > 0) {
-            tmem_ld_x32(tO + c * 32, o);
-            tmem_wait_ld();
-          } else {
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            if (nt > 0) {
+              tmem_ld_x32(tO + c * 32, o);
+              tmem_wait_ld();
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0u;
+              for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
+            if (row_ok) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                uint4 pk;
+                pk.x = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
+                pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
+                pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
+                pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
+                *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
+              }
+            }
           }
-          if (row_ok) {
+        } else {
+          // ---- accumulate mode: (O / l, LSE) of this key block is merged into the running fp32 (O, LSE) in place:
+          //   lse = logaddexp(lse_acc, lse_new);  o_acc = o_acc * exp(lse_acc - lse) + (O / l) * exp(lse_new - lse)
+          // (kernels/triton/attention_kernels.py:1567-1585). A side with LSE = -inf contributes nothing. ----
+          float* lrow = p.lse_acc + static_cast<int64_t>(w.batch) * p.lse_sb + static_cast<int64_t>(w.head) * p.lse_sh + q_row;
+          float* arow = p.o_acc + static_cast<int64_t>(w.batch) * p.acc_sb + static_cast<int64_t>(q_row) * p.acc_ss +
+                        static_cast<int64_t>(w.head) * p.acc_sh;
+          float w_old = 0.f, w_new = inv_l, lse_out = lse_val;
+          if (!p.acc_init && row_ok) {
+            const float lse_old = *lrow;
+            const float mx = fmaxf(lse_old, lse_val);
+            if (mx == -INFINITY) {
+              w_old = 0.f;
+              w_new = 0.f;
+              lse_out = -INFINITY;
+            } else {
+              const float e_old = fast_exp2((lse_old - mx) * kLog2e);
+              const float e_new = fast_exp2((lse_val - mx) * kLog2e);
+              const float den = e_old + e_new;
+              lse_out = mx + log2f(den) * kLn2;
+              w_old = e_old / den;
+              w_new = e_new / den * inv_l;
+            }
+          }
+          // a merge with a block that has no visible key for this row leaves the accumulator untouched
+          const bool touch = row_ok && (p.acc_init || lse_val != -INFINITY);
+          if (touch) *lrow = lse_out;
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 pk;
-              pk.x = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
-              pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
-              pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
-              pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            if (nt > 0) {
+              tmem_ld_x32(tO + c * 32, o);
+              tmem_wait_ld();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
+            if (touch) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                float4* dst = reinterpret_cast<float4*>(arow + c * 32 + q4 * 4);
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!p.acc_init) a = *dst;
+                a.x = a.x * w_old + __uint_as_float(o[q4 * 4 + 0]) * w_new;
+                a.y = a.y * w_old + __uint_as_float(o[q4 * 4 + 1]) * w_new;
+                a.z = a.z * w_old + __uint_as_float(o[q4 * 4 + 2]) * w_new;
+                a.w = a.w * w_old + __uint_as_float(o[q4 * 4 + 3]) * w_new;
+                *dst = a;
+              }
             }
           }
         }
@@ -571,9 +630,9 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   }
 }
 
-template <int D, typename T>
+template <int D, typename T, bool ACCUM>
 int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t stream) {
-  auto kern = fa_fwd_kernel<D, T>;
+  auto kern = fa_fwd_kernel<D, T, ACCUM>;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM_BYTES));
@@ -609,12 +668,14 @@ extern "C" int b200_debug_fa_trace(long long* dev_buf) {
 }
 #endif
 
-extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Sq, int Sk,
-                           int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3],
-                           const int64_t v_strides[3], const int64_t o_strides[3], float softmax_scale, int causal,
-                           int64_t causal_offset, const int32_t* kv_lens, int dtype, void* stream) {
-  using namespace b200;
-  B200_CHECK_ARG(q && k && v && o && q_strides && k_strides && v_strides && o_strides, "fa_fwd: NULL pointer argument");
+namespace b200 {
+namespace fa {
+
+// shared host path of b200_fa_fwd (16-bit output) and b200_fa_fwd_accum (merge into an fp32 accumulator)
+static int run(const void* q, const void* k, const void* v, int B, int Sq, int Sk, int Hq, int Hkv, int D,
+               const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3], float softmax_scale,
+               int causal, int64_t causal_offset, const int32_t* kv_lens, int dtype, void* stream, Params p, bool accum) {
+  B200_CHECK_ARG(q && k && v && q_strides && k_strides && v_strides, "fa_fwd: NULL pointer argument");
   B200_CHECK_ARG(B > 0 && Sq > 0 && Sk > 0 && Hq > 0 && Hkv > 0, "fa_fwd: bad sizes B=%d Sq=%d Sk=%d Hq=%d Hkv=%d", B, Sq,
                  Sk, Hq, Hkv);
   B200_CHECK_ARG(Hq % Hkv == 0, "fa_fwd: Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
@@ -624,31 +685,68 @@ extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o,
   B200_CHECK_ARG(B <= 65535 && Hq <= 65535, "fa_fwd: B and Hq must be <= 65535");
   CUtensorMap tq, tk, tv;
   int rc;
-  if ((rc = fa::make_bshd_tmap(&tq, q, B, Sq, Hq, D, q_strides, "q"))) return rc;
-  if ((rc = fa::make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
-  if ((rc = fa::make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
+  if ((rc = make_bshd_tmap(&tq, q, B, Sq, Hq, D, q_strides, "q"))) return rc;
+  if ((rc = make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
+  if ((rc = make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
+  // B200_FA_PERSISTENT=0 in the environment: every CTA handles only its own block (no work stealing)
+  static const bool persistent = [] { const char* e = getenv("B200_FA_PERSISTENT"); return !(e && e[0] == '0'); }();
+  p.persistent = persistent ? 1 : 0;
+  p.kv_lens = kv_lens;
+  p.B = B; p.Sq = Sq; p.Sk = Sk; p.Hq = Hq; p.Hkv = Hkv;
+  p.scale_log2 = softmax_scale * kLog2e;
+  p.causal = causal ? 1 : 0;
+  p.causal_offset = causal_offset;
+  p.num_pairs = (Sq + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf = dtype == B200_DTYPE_BF16;
+  if (accum) {
+    if (D == 128) return bf ? launch<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<128, __half, true>(tq, tk, tv, p, s);
+    return bf ? launch<64, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<64, __half, true>(tq, tk, tv, p, s);
+  }
+  if (D == 128) return bf ? launch<128, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch<128, __half, false>(tq, tk, tv, p, s);
+  return bf ? launch<64, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch<64, __half, false>(tq, tk, tv, p, s);
+}
+
+}  // namespace fa
+}  // namespace b200
+
+extern "C" int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Sq, int Sk,
+                           int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                           const int64_t v_strides[3], const int64_t o_strides[3], float softmax_scale, int causal,
+                           int64_t causal_offset, const int32_t* kv_lens, int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(o && o_strides, "fa_fwd: NULL output argument");
   for (int i = 0; i < 3; ++i)
     B200_CHECK_ARG(o_strides[i] > 0 && o_strides[i] % 8 == 0, "fa_fwd: o stride %d = %lld must be a positive multiple of 8 elements",
                    i, (long long)o_strides[i]);
   B200_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "fa_fwd: o must be 16-byte aligned");
-  fa::Params p;
+  fa::Params p{};
   p.o = o;
-  p.o_sb = o_strides[0]; p.o_ss = o_strides[1]; p.o_sh = o_strides[2];
-  // B200_FA_PERSISTENT=0 in the environment: every CTA handles only its own block (no work stealing)
-  static const bool persistent = [] { const char* e = getenv("B200_FA_PERSISTENT"); return !(e && e[0] == '0'); }();
-  p.persistent = persistent ? 1 : 0;
+  p.o_sb = o_strides[0]; p.o_sh = o_strides[2]; p.o_ss = o_strides[1];
   p.lse = lse;
-  p.kv_lens = kv_lens;
-  p.B = B; p.Sq = Sq; p.Sk = Sk; p.Hq = Hq; p.Hkv = Hkv;
-  p.scale_log2 = softmax_scale * fa::kLog2e;
-  p.causal = causal ? 1 : 0;
-  p.causal_offset = causal_offset;
-  p.num_pairs = (Sq + 2 * fa::BLOCK_M - 1) / (2 * fa::BLOCK_M);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (D == 128) {
-    return dtype == B200_DTYPE_BF16 ? fa::launch<128, __nv_bfloat16>(tq, tk, tv, p, s)
-                                    : fa::launch<128, __half>(tq, tk, tv, p, s);
-  }
-  return dtype == B200_DTYPE_BF16 ? fa::launch<64, __nv_bfloat16>(tq, tk, tv, p, s)
-                                  : fa::launch<64, __half>(tq, tk, tv, p, s);
+  return fa::run(q, k, v, B, Sq, Sk, Hq, Hkv, D, q_strides, k_strides, v_strides, softmax_scale, causal, causal_offset, kv_lens,
+                 dtype, stream, p, false);
+}
+
+extern "C" int b200_fa_fwd_accum(const void* q, const void* k, const void* v, float* o_acc, float* lse_acc, int B, int Sq,
+                                 int Sk, int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                                 const int64_t v_strides[3], const int64_t acc_strides[3], const int64_t lse_strides[2],
+                                 float softmax_scale, int causal, int64_t causal_offset, const int32_t* kv_lens, int init,
+                                 int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(o_acc && lse_acc && acc_strides && lse_strides, "fa_fwd_accum: NULL accumulator argument");
+  for (int i = 0; i < 3; ++i)
+    B200_CHECK_ARG(acc_strides[i] > 0 && acc_strides[i] % 4 == 0,
+                   "fa_fwd_accum: accumulator stride %d = %lld must be a positive multiple of 4 elements", i,
+                   (long long)acc_strides[i]);
+  B200_CHECK_ARG(lse_strides[0] > 0 && lse_strides[1] >= Sq, "fa_fwd_accum: bad LSE strides");
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(o_acc) & 15) == 0, "fa_fwd_accum: o_acc must be 16-byte aligned");
+  fa::Params p{};
+  p.o_acc = o_acc;
+  p.acc_sb = acc_strides[0]; p.acc_ss = acc_strides[1]; p.acc_sh = acc_strides[2];
+  p.lse_acc = lse_acc;
+  p.lse_sb = lse_strides[0]; p.lse_sh = lse_strides[1];
+  p.acc_init = init ? 1 : 0;
+  return fa::run(q, k, v, B, Sq, Sk, Hq, Hkv, D, q_strides, k_strides, v_strides, softmax_scale, causal, causal_offset, kv_lens,
+                 dtype, stream, p, true);
 }

@@ -13,6 +13,7 @@ Function ↔ reference map (paths under the reference tree):
 """
 from __future__ import annotations
 
+import ctypes
 import math
 from typing import Optional, Tuple
 
@@ -105,6 +106,41 @@ def flash_attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bo
                              _stream_ptr(dev))
     check("b200_fa_fwd", rc)
     return (out, lse) if return_lse else out
+
+
+def flash_attn_fwd_accum(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_acc: torch.Tensor, lse_acc: torch.Tensor,
+                         init: bool, causal: bool = False, softmax_scale: Optional[float] = None, causal_offset: int = 0,
+                         kv_lens: Optional[torch.Tensor] = None) -> None:
+    """One ring step: attention of q over this key block, merged in the kernel epilogue into the running fp32
+    ``o_acc [B,Sq,Hq,D]`` (any batch/seq/head strides, D contiguous) and ``lse_acc [B,Hq,Sq]`` (rows contiguous).
+    ``init=True`` overwrites the accumulator (first step), otherwise the block is log-sum-exp merged into it."""
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError(f"expected 4-D [B,S,H,D] tensors, got {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    dev = _require_cuda(q, k, v, o_acc, lse_acc, kv_lens)
+    B, Sq, Hq, D = q.shape
+    Bk, Sk, Hkv, Dk = k.shape
+    if (Bk, Dk) != (B, D) or tuple(v.shape) != tuple(k.shape):
+        raise ValueError(f"q/k/v shapes do not match: {tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    if k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError("q, k, v must share a dtype")
+    if o_acc.dtype != torch.float32 or tuple(o_acc.shape) != (B, Sq, Hq, D) or o_acc.stride(-1) != 1:
+        raise ValueError("o_acc must be fp32 [B,Sq,Hq,D] with a contiguous head dimension")
+    if lse_acc.dtype != torch.float32 or tuple(lse_acc.shape) != (B, Hq, Sq) or lse_acc.stride(-1) != 1:
+        raise ValueError("lse_acc must be fp32 [B,Hq,Sq] with contiguous rows")
+    dt = _dtype_code(q)
+    q, k, v = _last_dim_contiguous(q), _last_dim_contiguous(k), _last_dim_contiguous(v)
+    if kv_lens is not None:
+        if kv_lens.dtype != torch.int32 or kv_lens.numel() != B or not kv_lens.is_contiguous():
+            raise ValueError("kv_lens must be a contiguous int32 tensor of shape [B]")
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+    lse_strides = (ctypes.c_int64 * 2)(int(lse_acc.stride(0)), int(lse_acc.stride(1)))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_fa_fwd_accum(q.data_ptr(), k.data_ptr(), v.data_ptr(), o_acc.data_ptr(), lse_acc.data_ptr(), B, Sq, Sk,
+                                   Hq, Hkv, D, strides3(q.stride()[:3]), strides3(k.stride()[:3]), strides3(v.stride()[:3]),
+                                   strides3(o_acc.stride()[:3]), lse_strides, scale, int(bool(causal)), int(causal_offset),
+                                   _ptr(kv_lens), int(bool(init)), dt, _stream_ptr(dev))
+    check("b200_fa_fwd_accum", rc)
 
 
 def lse_merge(o_acc: torch.Tensor, lse_acc: torch.Tensor, o_b: torch.Tensor, lse_b: torch.Tensor) -> None:

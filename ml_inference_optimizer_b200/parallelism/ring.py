@@ -34,6 +34,11 @@ class CudaRingBackend:
         from .. import ops
         return ops.flash_attn_fwd(q, k, v, causal=causal, softmax_scale=softmax_scale, return_lse=True)
 
+    def attn_accum(self, q, k, v, o_acc, lse_acc, init: bool, causal: bool, softmax_scale: Optional[float]) -> None:
+        """One ring step fused: K1 with the log-sum-exp merge into (o_acc fp32, lse_acc) in its epilogue."""
+        from .. import ops
+        ops.flash_attn_fwd_accum(q, k, v, o_acc, lse_acc, init, causal=causal, softmax_scale=softmax_scale)
+
     def merge(self, o_acc, lse_acc, o_b, lse_b) -> None:
         from .. import ops
         ops.lse_merge(o_acc, lse_acc, o_b, lse_b)
@@ -68,6 +73,43 @@ class _Acc:
         return self.backend.finalize(self.o, dtype), self.lse
 
 
+def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap, return_lse, n, r):
+    """Ring with the merge fused into the attention kernel (``backend.attn_accum``): one launch per step, one fp32
+    accumulator for all local query rows, no 16-bit partial outputs, no separate merge / slice / concatenate kernels.
+    Step 0 is always the rank's own block (src == r), which touches every local query row, so it initialises the
+    accumulator; every later step merges. Steps that only concern a part of the rows (zigzag, src > r) are given the
+    views of that part."""
+    B, S, Hq, D = q.shape
+    half = S // 2
+    kv = [torch.stack([k, v]).contiguous(), None]
+    kv[1] = torch.empty_like(kv[0])
+    exchange = RingExchange(group, use_side_stream=overlap)
+    o_acc = torch.empty(B, S, Hq, D, dtype=torch.float32, device=q.device)
+    lse_acc = torch.empty(B, Hq, S, dtype=torch.float32, device=q.device)
+    for step in range(n):
+        cur = kv[step % 2]
+        if step + 1 < n:
+            exchange.start([cur], [kv[(step + 1) % 2]])  # overlaps with the attention below
+        src = (r - step) % n
+        kc, vc = cur[0], cur[1]
+        init = step == 0
+        if not causal:
+            backend.attn_accum(q, kc, vc, o_acc, lse_acc, init, False, softmax_scale)
+        elif src == r:
+            backend.attn_accum(q, kc, vc, o_acc, lse_acc, init, True, softmax_scale)
+        elif zigzag:
+            if src < r:   # all local queries x first half of the visiting keys
+                backend.attn_accum(q, kc[:, :half], vc[:, :half], o_acc, lse_acc, init, False, softmax_scale)
+            else:         # second half of the local queries x all visiting keys
+                backend.attn_accum(q[:, half:], kc, vc, o_acc[:, half:], lse_acc[:, :, half:], init, False, softmax_scale)
+        elif src < r:     # causal, contiguous shards: earlier ranks are fully visible, later ranks not at all
+            backend.attn_accum(q, kc, vc, o_acc, lse_acc, init, False, softmax_scale)
+        if step + 1 < n:
+            exchange.wait()
+    out = backend.finalize(o_acc, q.dtype)
+    return (out, lse_acc) if return_lse else out
+
+
 def ring_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False,
                            softmax_scale: Optional[float] = None, group=None, partition: str = "contiguous",
                            backend=None, overlap: bool = True, return_lse: bool = False):
@@ -86,6 +128,8 @@ def ring_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, ca
     if partition == "zigzag" and S % 2 != 0:
         raise ValueError("the zigzag partition needs an even local sequence length")
     half = S // 2
+    if hasattr(backend, "attn_accum"):
+        return _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap, return_lse, n, r)
 
     # KV double buffer: cur is attended to while nxt is being received
     kv = [torch.stack([k, v]).contiguous(), None]

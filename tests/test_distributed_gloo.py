@@ -36,6 +36,20 @@ class OracleRingBackend:
         return o_acc.to(dtype)
 
 
+class OracleFusedRingBackend(OracleRingBackend):
+    """The fused-step protocol of CudaRingBackend (``attn_accum``: attention + merge into the accumulator views)."""
+
+    def attn_accum(self, q, k, v, o_acc, lse_acc, init, causal, softmax_scale):
+        o, lse = orc.attention_ref(q, k, v, causal=causal, softmax_scale=softmax_scale)
+        if init:
+            o_acc.copy_(o)
+            lse_acc.copy_(lse)
+        else:
+            mo, ml = orc.lse_merge_ref(o_acc, lse_acc, o, lse)
+            o_acc.copy_(mo)
+            lse_acc.copy_(ml)
+
+
 def _worker(rank, world, port, fn_name, return_dict):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -71,6 +85,10 @@ def _ring_case(rank, world):
             sh = lambda t: comm.scatter_along_sequence_dim(t, world, partition=part, rank=rank).contiguous()
             o, lse = ring_attention_forward(sh(q), sh(k), sh(v), causal=causal, partition=part, backend=OracleRingBackend(),
                                             overlap=False, return_lse=True)
+            # the fused-step path (one accumulator, views for partial steps) must give the same shard
+            o2, lse2 = ring_attention_forward(sh(q), sh(k), sh(v), causal=causal, partition=part,
+                                              backend=OracleFusedRingBackend(), overlap=False, return_lse=True)
+            errs[(causal, part, "fused")] = max(float((o2 - o).abs().max()), float((lse2 - lse).abs().max()))
             want = sh(full)
             want_lse = comm.scatter_along_sequence_dim(lse_full.transpose(1, 2), world, partition=part, rank=rank).transpose(1, 2)
             errs[(causal, part)] = (float((o - want).abs().max()), float((lse - want_lse).abs().max()))

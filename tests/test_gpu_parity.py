@@ -103,6 +103,37 @@ def test_fa_fwd_work_stealing_many_items(ops, B, S, H, Hkv, D, causal, kv_lens):
     check_lse(lse, rl)
 
 
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hkv,D,causal", [
+    (2, 512, 1024, 4, 2, 128, False),
+    (1, 384, 768, 2, 2, 64, False),
+    (2, 512, 512, 4, 4, 128, True),      # causal: second key block partly / fully invisible for early rows
+])
+def test_fa_fwd_accum_key_blocks_equal_full_attention(ops, B, Sq, Sk, Hq, Hkv, D, causal):
+    """Accumulate mode (one ring step per call): attending to the key blocks one after the other, each merged into the
+    fp32 accumulator in the kernel epilogue, equals attention over all keys — including rows for which a later block
+    is fully masked (accumulator untouched) and views of the accumulator for a subset of the rows."""
+    q, k, v = rand_qkv(B, Sq, Sk, Hq, Hkv, D, seed=3)
+    off = Sk - Sq if causal else 0      # bottom-right aligned causal mask over the concatenated keys
+    o_acc = torch.full((B, Sq, Hq, D), float("nan"), device="cuda", dtype=torch.float32)
+    lse_acc = torch.full((B, Hq, Sq), float("nan"), device="cuda", dtype=torch.float32)
+    cuts = [0, Sk // 4, Sk // 4 + 128, Sk]
+    for i, (a, b) in enumerate(zip(cuts, cuts[1:])):
+        ops.flash_attn_fwd_accum(q, k[:, a:b], v[:, a:b], o_acc, lse_acc, init=(i == 0), causal=causal, causal_offset=off - a)
+    ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=causal, causal_offset=off)
+    check_out(ops.cast_out(o_acc, q.dtype), ro)
+    check_lse(lse_acc, rl)
+    # a step that only concerns the second half of the rows, through views (zigzag ring, src > r)
+    h = Sq // 2
+    o2 = torch.zeros_like(o_acc)
+    l2 = torch.full_like(lse_acc, float("-inf"))
+    ops.flash_attn_fwd_accum(q[:, h:], k, v, o2[:, h:], l2[:, :, h:], init=True, causal=False)
+    ops.flash_attn_fwd_accum(q[:, h:], k, v, o2[:, h:], l2[:, :, h:], init=False, causal=False)  # same block twice
+    ro2, rl2 = orc.attention_ref(q[:, h:].cpu(), k.cpu(), v.cpu())
+    check_out(o2[:, h:], ro2)                                    # merging a block with itself leaves O unchanged
+    assert (l2[:, :, h:].cpu() - (rl2 + math.log(2.0))).abs().max().item() <= LSE_MAX_ABS   # and adds ln 2 to the LSE
+    assert torch.all(o2[:, :h] == 0) and torch.all(torch.isinf(l2[:, :, :h]))               # other rows untouched
+
+
 def test_fa_fwd_fp16(ops):
     q, k, v = rand_qkv(1, 512, 512, 2, 2, 128, dtype=torch.float16)
     o, lse = ops.flash_attn_fwd(q, k, v, causal=True, return_lse=True)
