@@ -70,7 +70,9 @@ def main():
     y_plain = m(c(xl))  # one fused call + one all-reduce: the chunked pipeline must agree with it up to the reduction order
     e2 = (y.float() - y_plain.float()).abs().max().item()
     # partial sums are rounded to bf16 before the all-reduce (the reference reduces in the activation dtype too)
-    good = e <= 2e-2 * max(1.0, ref.abs().max().item() / 4) * (1 + world / 4) and e2 <= 2e-2
+    # (so two all-reduce schedules differ by the bf16 rounding of `world` partial sums: same scale for both bounds)
+    tol = 2e-2 * max(1.0, ref.abs().max().item() / 4) * (1 + world / 4)
+    good = e <= tol and e2 <= tol
     ok &= good
     print(f"[rank {rank}] tp mlp swiglu overlapped (T={xl.shape[0]}): max|dy|={e:.2e} vs single all-reduce {e2:.2e} "
           f"{'OK' if good else 'FAIL'}", flush=True)
