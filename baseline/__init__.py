@@ -9,4 +9,7 @@ inference = _mod
 _mu = importlib.import_module("ml_inference_optimizer_b200.baseline.model_utils")
 sys.modules[f"{__name__}.model_utils"] = _mu
 model_utils = _mu
+_ml = importlib.import_module("ml_inference_optimizer_b200.baseline.model_loader")
+sys.modules[f"{__name__}.model_loader"] = _ml
+model_loader = _ml
 from ml_inference_optimizer_b200.baseline import *  # noqa: F401,F403,E402

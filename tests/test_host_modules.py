@@ -268,3 +268,40 @@ def test_add_paged_attention_requires_attention_layers():
 
     with pytest.raises(ValueError):
         add_paged_attention_to_model(torch.nn.Sequential(torch.nn.Linear(4, 4)))
+
+
+def test_model_loader_registry_and_random_init():
+    """``baseline.model_loader.load_model`` returns ``(model, loader)`` (reference baseline/model_loader.py:466-489); without
+    network the HF loader builds the named architecture from its config with seeded random weights."""
+    from baseline.model_loader import (BaseModelLoader, TorchModelLoader, load_model, model_registry, register_custom_loader,
+                                       register_custom_pattern)
+
+    model, loader = load_model("gpt2", device="cpu", dtype=torch.float32, random_init=True,
+                               config_overrides={"n_layer": 1, "n_embd": 64, "n_head": 4, "vocab_size": 97})
+    assert type(model).__name__ == "GPT2LMHeadModel" and loader.get_model_config()["n_layer"] == 1
+    ids = loader.get_sample_input(2, 5)
+    assert ids.shape == (2, 5) and int(ids.max()) < 97
+    with torch.no_grad():
+        assert model(ids).logits.shape == (2, 5, 97)
+    m2, _ = load_model("gpt2", device="cpu", random_init=True, config_overrides={"n_layer": 1, "n_embd": 64, "n_head": 4, "vocab_size": 97})
+    assert torch.equal(m2.transformer.wte.weight, model.transformer.wte.weight)  # seeded
+
+    class Toy(BaseModelLoader):
+        def __init__(self, device="cpu", dtype=None):
+            self.device = device
+        def load_model(self, model_name, **kw):
+            return nn.Linear(3, 3)
+        def get_sample_input(self, b, s):
+            return torch.zeros(b, 3)
+        def get_model_config(self):
+            return {"toy": True}
+
+    register_custom_loader("toy", Toy)
+    register_custom_pattern(r"^toy-.*", Toy)
+    assert "toy" in model_registry.list_registered_loaders()
+    m, l = load_model("toy-1", device="cpu")
+    assert isinstance(m, nn.Linear) and l.get_model_config() == {"toy": True}
+    m, l = load_model("whatever", loader_name="torch", device="cpu", factory=lambda: nn.Linear(2, 2))
+    assert isinstance(l, TorchModelLoader) and l.get_model_config()["parameters"] == 6
+    with pytest.raises(ValueError):
+        load_model("x", loader_name="nope", device="cpu")
