@@ -103,16 +103,20 @@ layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __
 }
 
 // narrow rows (cols <= 2048): one warp per row, 8 rows per CTA, no shared memory, shuffles only
-constexpr int W_MAX_ITERS = 8;  // cols <= 32 * VEC * W_MAX_ITERS = 2048
+constexpr int W_MAX_ITERS_LIMIT = 8;  // warp-per-row kernel: cols <= 32 * VEC * 8 = 2048
 
-template <typename T, bool HAS_RES>
+// ITERS = ceil(cols / 256) is a template parameter: the row lives in ITERS*8 registers per lane, so narrow rows (768
+// columns: 24 registers) leave room for 5+ resident CTAs per SM instead of the 2 a worst-case 2048-column row buffer
+// allows — the kernel is HBM-bound and needs the bytes in flight. The grid is persistent (warps stride over the rows).
+template <typename T, bool HAS_RES, int ITERS>
 __global__ void __launch_bounds__(THREADS)
 layernorm_warp_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, const T* __restrict__ b,
                       T* __restrict__ y, int64_t rows, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps,
                       float alpha) {
+  constexpr int W_MAX_ITERS = ITERS;
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (THREADS / 32);
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5); row < rows; row += warps_total) {
   const T* xr = x + row * ldx;
   const T* rr = HAS_RES ? res + row * ldr : nullptr;
   float v[W_MAX_ITERS][VEC];
@@ -182,6 +186,7 @@ layernorm_warp_kernel(const T* __restrict__ x, const T* __restrict__ res, const 
       *reinterpret_cast<uint4*>(yr + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
+  }  // row loop
 }
 
 }  // namespace ln
@@ -203,15 +208,26 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "layernorm: dtype must be bf16 or fp16");
   if (rows == 0) return B200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool narrow = cols <= 32 * ln::VEC * ln::W_MAX_ITERS;
-  const unsigned grid = narrow ? static_cast<unsigned>((rows + ln::THREADS / 32 - 1) / (ln::THREADS / 32))
+  const bool narrow = cols <= 32 * ln::VEC * ln::W_MAX_ITERS_LIMIT;
+  const int w_iters = (cols + 32 * ln::VEC - 1) / (32 * ln::VEC);
+  const int64_t warp_ctas = (rows + ln::THREADS / 32 - 1) / (ln::THREADS / 32);
+  const int64_t resident = static_cast<int64_t>(sm_count()) * 8;  // persistent: at most 8 CTAs of 256 threads per SM
+  const unsigned grid = narrow ? static_cast<unsigned>(warp_ctas < resident ? warp_ctas : resident)
                                : static_cast<unsigned>(rows);
-#define LAUNCH(T, HAS)                                                                                              \
-  if (narrow)                                                                                                          \
-    ln::layernorm_warp_kernel<T, HAS><<<grid, ln::THREADS, 0, s>>>(                                                  \
+#define LAUNCH_W(T, HAS, IT)                                                                                       \
+  case IT:                                                                                                             \
+    ln::layernorm_warp_kernel<T, HAS, IT><<<grid, ln::THREADS, 0, s>>>(                                                \
         static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
         static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);              \
-  else                                                                                                                 \
+    break;
+#define LAUNCH(T, HAS)                                                                                              \
+  if (narrow) {                                                                                                        \
+    switch (w_iters) {                                                                                                 \
+      LAUNCH_W(T, HAS, 1) LAUNCH_W(T, HAS, 2) LAUNCH_W(T, HAS, 3) LAUNCH_W(T, HAS, 4) LAUNCH_W(T, HAS, 5)              \
+      LAUNCH_W(T, HAS, 6) LAUNCH_W(T, HAS, 7) LAUNCH_W(T, HAS, 8)                                                      \
+      default: break;                                                                                                  \
+    }                                                                                                                  \
+  } else                                                                                                                 \
     ln::layernorm_kernel<T, HAS><<<grid, ln::THREADS, 0, s>>>(                                                        \
         static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
         static_cast<const T*>(bias), static_cast<T*>(y), cols, ldx, ldr, ldy, eps, residual_alpha)
@@ -221,6 +237,7 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
     if (residual) { LAUNCH(__half, true); } else { LAUNCH(__half, false); }
   }
 #undef LAUNCH
+#undef LAUNCH_W
   B200_CUDA_OK(cudaGetLastError());
   return B200_OK;
 }

@@ -1,0 +1,19 @@
+"""Dev tool: LayerNorm(+residual) bandwidth at the shapes the MLP/attention blocks see."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ml_inference_optimizer_b200 import ops
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for rows, cols in ((32768, 768), (32768, 1024), (32768, 2048), (32768, 4096), (32768, 8192)):
+    x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16); r = torch.randn_like(x)
+    w = torch.randn(cols, device="cuda", dtype=torch.bfloat16); b = torch.randn_like(w)
+    for res in (None, r):
+        ts = []
+        for _ in range(12):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); ops.layernorm(x, w, b, 1e-5, residual=res); e.record(); torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = sorted(ts)[len(ts) // 2]
+        nbytes = rows * cols * 2 * (2 + (res is not None))
+        print(f"LN rows={rows} cols={cols} residual={res is not None}: {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s", flush=True)
