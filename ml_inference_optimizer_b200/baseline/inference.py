@@ -115,6 +115,14 @@ class PagedKVCache:
             meta.append_block(self.block_manager.allocate_block())
         meta.logical_len = max(meta.logical_len, num_tokens)
 
+    def reserve_blocks(self, seq_id: int, num_tokens: int) -> None:
+        """Allocate the blocks that ``num_tokens`` tokens will need without changing the sequence length, so the block
+        table stays fixed while the tokens are appended (what a captured decode graph needs)."""
+        self._ensure_sequence_exists(seq_id)
+        meta = self.sequences[seq_id]
+        for _ in range(math.ceil(num_tokens / self.block_size) - len(meta)):
+            meta.append_block(self.block_manager.allocate_block())
+
     def append_token(self, seq_id: int) -> None:
         self._ensure_sequence_exists(seq_id)
         meta = self.sequences[seq_id]
@@ -249,10 +257,14 @@ def _adapters(model: nn.Module) -> List[_fa._HFAttentionAdapter]:
 
 
 def generate_paged(model: nn.Module, input_ids: torch.Tensor, max_new_tokens: int, cache: Optional[PagedKVCache] = None,
-                   block_size: int = 16) -> torch.Tensor:
+                   block_size: int = 16, use_cuda_graph: bool = False) -> torch.Tensor:
     """Greedy generation with the paged KV cache: prefill runs K1 and scatters the prompt's K,V into blocks; every decode
     step appends the new token's K,V (``b200_kv_append``) and attends through the block tables (K2). Returns
-    ``[B, S + max_new_tokens]`` token ids."""
+    ``[B, S + max_new_tokens]`` token ids.
+
+    ``use_cuda_graph=True`` captures one decode step (all layers: projections, KV append, K2, MLP, LM head, argmax) in a
+    CUDA graph and replays it: block tables are reserved up front, lengths / positions / the token are advanced on the
+    device, so a step has no host work besides the replay (the loop is launch-bound otherwise)."""
     adapters = _adapters(model)
     first = adapters[0].inner
     B, S = input_ids.shape
@@ -271,6 +283,8 @@ def generate_paged(model: nn.Module, input_ids: torch.Tensor, max_new_tokens: in
             logits = model(input_ids, use_cache=False).logits
             nxt = logits[:, -1].argmax(-1, keepdim=True)
             out = torch.cat([out, nxt], dim=1)
+            if use_cuda_graph and max_new_tokens > 1:
+                return torch.cat([out, _decode_with_graph(model, cache, seq_ids, nxt, S, max_new_tokens - 1)], dim=1)
             for step in range(1, max_new_tokens):
                 for sid in seq_ids:
                     cache.append_token(sid)
@@ -284,3 +298,75 @@ def generate_paged(model: nn.Module, input_ids: torch.Tensor, max_new_tokens: in
     finally:
         _fa.set_paged_context(None)
     return out
+
+
+def _decode_with_graph(model: nn.Module, cache: PagedKVCache, seq_ids: List[int], first_token: torch.Tensor, prompt_len: int,
+                       steps: int, eager_steps: int = 2) -> torch.Tensor:
+    """``steps`` greedy decode steps after the prefill; returns the generated ids ``[B, steps]``. The first
+    ``eager_steps`` run eagerly (they also size the kernel workspaces), then one step is captured and replayed."""
+    B = first_token.shape[0]
+    dev = first_token.device
+    total = prompt_len + steps + 1
+    for sid in seq_ids:
+        cache.reserve_blocks(sid, total)
+    bt, lens = cache.device_tables(seq_ids)            # fixed block tables; lens = prompt length
+    tok = first_token.clone()
+    pos = torch.full((B, 1), prompt_len, dtype=torch.long, device=dev)
+    out_buf = torch.zeros(B, steps, dtype=torch.long, device=dev)
+    idx = torch.zeros(1, 1, dtype=torch.long, device=dev)
+    _fa.set_paged_context({"mode": "decode", "cache": cache, "seq_ids": seq_ids, "block_tables": bt, "context_lengths": lens,
+                           "max_context_len": total})
+
+    def step():
+        lens.add_(1)                                   # the token appended in this step counts (attention_kernels.py:862-866)
+        logits = model(tok, position_ids=pos, use_cache=False).logits
+        n = logits[:, -1].argmax(-1, keepdim=True)
+        tok.copy_(n)
+        pos.add_(1)
+        out_buf.scatter_(1, idx.expand(B, 1), n)
+        idx.add_(1)
+
+    # The attention blocks of a converted model mask inside the kernels; HF's "eager" mask builder would still create a
+    # dense additive mask per step (with a host scalar -> device copy, which a capture forbids). The "sdpa" mask interface
+    # returns None for a single un-padded query token, so it is selected for the duration of the decode loop.
+    configs = {id(m.config): m.config for m in model.modules() if hasattr(getattr(m, "config", None), "_attn_implementation")}
+    saved_impl = {k: c._attn_implementation for k, c in configs.items()}
+    for c in configs.values():
+        c._attn_implementation = "sdpa"
+    try:
+        return _decode_with_graph_body(step, steps, eager_steps, dev, cache, seq_ids, out_buf)
+    finally:
+        for k, c in configs.items():
+            c._attn_implementation = saved_impl[k]
+
+
+#: timing of the last captured decode loop (device time): {"replay_steps", "replay_ms", "capture_s"}
+LAST_DECODE_STATS: Dict[str, float] = {}
+
+
+def _decode_with_graph_body(step, steps, eager_steps, dev, cache, seq_ids, out_buf):
+    done = 0
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):                      # warm-up on the stream the capture will use
+        for _ in range(min(eager_steps, steps)):
+            step()
+            done += 1
+    torch.cuda.current_stream(dev).wait_stream(side)
+    if done < steps:
+        t0 = time.perf_counter()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            step()
+        capture_s = time.perf_counter() - t0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps - done):
+            graph.replay()
+        e1.record()
+        e1.synchronize()
+        LAST_DECODE_STATS.update(replay_steps=steps - done, replay_ms=e0.elapsed_time(e1), capture_s=capture_s)
+    for sid in seq_ids:                                # host bookkeeping of the lengths (blocks are already there)
+        for _ in range(steps):
+            cache.append_token(sid)
+    return out_buf

@@ -298,7 +298,7 @@ class _HFAttentionAdapter(nn.Module):
                 ops.kv_append(k[:, 0], v[:, 0], kc, vc, ctx_["context_lengths"], ctx_["block_tables"], self.layer_idx)
                 attn = ops.decode_attention(q[:, 0].contiguous(), kc, vc, ctx_["context_lengths"],
                                             softmax_scale=inner.config.softmax_scale, block_tables=ctx_["block_tables"],
-                                            layer_idx=self.layer_idx).unsqueeze(1)
+                                            layer_idx=self.layer_idx, max_context_len=ctx_.get("max_context_len")).unsqueeze(1)
             out = inner.o_proj(attn.reshape(B, S, inner.hidden_size).to(orig))
             return (out,) + (None,) * (self.returns_tuple_len - 1)
         if cache is not None and hasattr(cache, "update"):

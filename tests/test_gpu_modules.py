@@ -274,3 +274,26 @@ def test_add_paged_attention_to_model_and_benchmark_runner(tmp_path):
             assert key in res[variant], (variant, key)
         assert res[variant]["avg_latency_ms"] > 0
     assert any(f.endswith("_gpt2-2l.json") for f in os.listdir(tmp_path))
+
+
+def test_paged_generation_cuda_graph_matches_eager():
+    """The decode step captured in a CUDA graph (block tables reserved up front, lengths / positions / token advanced on
+    the device) generates exactly the tokens of the step-by-step loop, and leaves the cache bookkeeping in the same state."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from baseline.inference import PagedKVCache, generate_paged
+    from ml_inference_optimizer import Optimizer
+
+    torch.manual_seed(0)
+    cfg = GPT2Config(n_layer=2, attn_implementation="eager")
+    model = Optimizer(GPT2LMHeadModel(cfg).eval().to("cuda", torch.bfloat16)).optimize()
+    ids = torch.randint(0, cfg.vocab_size, (2, 21), device="cuda")
+    mk = lambda: PagedKVCache(num_blocks=12, block_size=16, num_layers=2, num_heads=12, head_dim=64, dtype=torch.bfloat16,
+                              device="cuda")
+    c1, c2 = mk(), mk()
+    eager = generate_paged(model, ids, 14, cache=c1)
+    graph = generate_paged(model, ids, 14, cache=c2, use_cuda_graph=True)
+    assert graph.shape == eager.shape == (2, 35)
+    assert torch.equal(graph, eager)
+    assert c2.get_sequence_length(0) == c1.get_sequence_length(0) == 21 + 13
+    assert len(c2.get_block_table(1)) == 3
