@@ -8,7 +8,7 @@
  * Conventions
  *   - extern "C", plain pointers and sizes, no torch / C++ types. Returns 0 (B200_OK) or a negative error
  *     code; b200_last_error() returns a thread-local description. Never throws, never allocates or frees
- *     caller memory, never synchronises the device (except b200_selftest_sync helpers that say so).
+ *     caller memory, never synchronises the device.
  *   - All data pointers are DEVICE pointers. Strides are in ELEMENTS. `stream` is a cudaStream_t passed as
  *     void* (NULL = legacy default stream).
  *   - dtype: B200_DTYPE_BF16 or B200_DTYPE_FP16 for q/k/v/o/x/weights; statistics (LSE) and split-K partials
