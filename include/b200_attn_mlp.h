@@ -62,6 +62,19 @@ int b200_arch_ok(void);
  * serialisation, parallelism/tensor_parallel.py:302 rebuilt). */
 int b200_set_sm_limit(int max_ctas);
 
+/* L2 rasterisation of the persistent GEMM kernels: output tiles are visited in groups that cover `rows` rows of the
+ * activation: the group's activation panel stays L2-resident while the weight is streamed once per group, so DRAM reads
+ * ~ x + W * ceil(T / rows). rows = 0 (default) picks the largest group whose per-wave footprint fits a 48 MB L2 budget
+ * (measured, csrc/gemm_mlp.cu choose_group_m); otherwise rows >= 256. (The reference's Triton kernels have no such
+ * control: kernels/triton/mlp_kernels.py uses a plain 2-D grid, :690-705.) */
+int b200_set_gemm_group_rows(int rows);
+
+/* Measurement hooks (the reference's BenchmarkRunner counts nothing, benchmarks/runners.py:185-248): number of kernel
+ * launches this library has issued in the process so far, and the name of the GEMM kernel the last linear / FusedMLP
+ * call dispatched to (static string). */
+int64_t b200_launch_count(void);
+const char* b200_last_gemm_kernel(void);
+
 /* ---- K1: tiled online-softmax attention forward (prefill) -------------------------------------------
  * Replaces triton_flash_attention / _flash_attention_forward_kernel
  *   (kernels/triton/flash_attention_kernels.py:1150-1358, :38-325), the attention inside
@@ -179,6 +192,25 @@ int b200_linear_act(const void* x, int64_t ldx, const void* w, const void* b, co
 int b200_layernorm(const void* x, const void* residual, const void* weight, const void* bias, void* y, int64_t rows,
                    int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps, float residual_alpha, int dtype,
                    void* stream);
+
+/* ---- K6: tensor-parallel all-reduce over NVSwitch multicast / peer memory -------------------------------
+ * Replaces torch.distributed.all_reduce(output_parallel) + the bias add of RowParallelLinear.forward
+ * (parallelism/tensor_parallel.py:296-308) and comm.all_reduce (parallelism/communication.py:37-209) for the
+ * row-parallel down projection of the FusedMLP.
+ *
+ * In-place two-shot all-reduce (sum) of the byte range [data_offset, data_offset + nbytes) of a SYMMETRIC buffer:
+ * a buffer of identical size on every rank, mapped into this process once per peer (`peer_bases[world]`, HOST array of
+ * device pointers, own rank included) and — when the fabric supports it — once as a multicast address
+ * (`multicast_base`, NULL selects the unicast peer load/store path). Rank r reduces slice r with
+ * multimem.ld_reduce (fp32 accumulation inside the switch), optionally adds `bias` ([ncols], region = whole rows of
+ * ncols elements) and broadcasts it with multimem.st. `flag_offset` names b200_tp_allreduce_flag_bytes() bytes inside
+ * the symmetric buffer, zeroed once at creation; `epoch` must advance by 2 per call on that buffer, identically on all
+ * ranks (the first call uses 1). All ranks must pass identical sizes and `max_ctas` (0 = 32; <= 64). Spins are bounded:
+ * on a timeout (a peer never arrived) *error_flag (device int) is set to 1 and the kernel returns.            */
+int64_t b200_tp_allreduce_flag_bytes(void);
+int b200_tp_allreduce(void* multicast_base, void* const* peer_bases, int world, int rank, int64_t data_offset,
+                      int64_t nbytes, int64_t flag_offset, uint32_t epoch, const void* bias, int ncols, int dtype,
+                      int max_ctas, int* error_flag, void* stream);
 
 #ifdef __cplusplus
 }

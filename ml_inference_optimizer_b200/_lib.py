@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import threading
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p, POINTER
 
 from .build import LIB_PATH
 
@@ -24,6 +24,9 @@ SIGNATURES = {
     "b200_last_error": (c_char_p, []),
     "b200_arch_ok": (c_int, []),
     "b200_set_sm_limit": (c_int, [c_int]),
+    "b200_set_gemm_group_rows": (c_int, [c_int]),
+    "b200_launch_count": (c_int64, []),
+    "b200_last_gemm_kernel": (c_char_p, []),
     "b200_fa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_float, c_int, c_int64, c_void_p, c_int,
                             c_void_p]),
@@ -45,6 +48,9 @@ SIGNATURES = {
                                c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),
     "b200_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64,
                                c_float, c_float, c_int, c_void_p]),
+    "b200_tp_allreduce_flag_bytes": (c_int64, []),
+    "b200_tp_allreduce": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_int, c_int64, c_int64, c_int64, c_uint32, c_void_p,
+                                  c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200_linear_act_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int]),
     "b200_linear_act": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                 c_int, c_int, c_int, c_void_p, c_int64, c_int, c_void_p]),

@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_NAME = "libb200_attn_mlp.so"
 LIB_PATH = PKG_DIR / LIB_NAME
-SOURCES = ["host_common.cu", "fa_fwd.cu", "fa_decode.cu", "gemm_mlp.cu", "ln_kernels.cu"]
+SOURCES = ["host_common.cu", "fa_fwd.cu", "fa_decode.cu", "gemm_mlp.cu", "ln_kernels.cu", "tp_allreduce.cu"]
 HEADERS = ["common.cuh", "host_common.h", "../../include/b200_attn_mlp.h"]
 
 NVCC_FLAGS = [

@@ -579,9 +579,11 @@ int launch_decode(const Params& p, bool paged, cudaStream_t stream) {
   if (paged) decode_kernel<D, G, T, true><<<grid, NUM_THREADS, 0, stream>>>(p);
   else decode_kernel<D, G, T, false><<<grid, NUM_THREADS, 0, stream>>>(p);
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("decode_kernel");
   if (p.splits > 1) {
     decode_reduce_kernel<D, T><<<p.B * p.Hq, D, 0, stream>>>(p.part_o, p.part_lse, p.o, p.lse, p.splits);
     B200_CUDA_OK(cudaGetLastError());
+    note_launch("decode_reduce_kernel");
   }
   return B200_OK;
 }
@@ -592,9 +594,11 @@ int launch_decode_gqa(int G, const Params& p, bool paged, cudaStream_t stream) {
   if (paged) decode_gqa_mma_kernel<D, T, true><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
   else decode_gqa_mma_kernel<D, T, false><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("decode_gqa_mma_kernel");
   if (p.splits > 1) {
     decode_reduce_kernel<D, T><<<p.B * p.Hq, D, 0, stream>>>(p.part_o, p.part_lse, p.o, p.lse, p.splits);
     B200_CUDA_OK(cudaGetLastError());
+    note_launch("decode_reduce_kernel");
   }
   return B200_OK;
 }
@@ -711,6 +715,7 @@ int b200_kv_append(const void* key, const void* value, void* k_cache, void* v_ca
       static_cast<uint16_t*>(v_cache), context_lens, Hkv * D, layout, kv_batch_stride, kv_token_stride, block_table,
       max_blocks_per_seq, block_size, num_layers, layer_idx);
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("kv_append_kernel");
   return B200_OK;
 }
 
@@ -736,6 +741,7 @@ int b200_lse_merge(float* o_acc, float* lse_acc, const void* o_b, const float* l
         o_acc, lse_acc, static_cast<const __half*>(o_b), lse_b, B, Sq, Hq, D, ob_strides[0], ob_strides[1],
         ob_strides[2]);
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("lse_merge_kernel");
   return B200_OK;
 }
 
@@ -759,6 +765,7 @@ int b200_cast_out(const float* o_acc, void* o, int B, int Sq, int Hq, int D, con
   else
     return set_error(B200_ERR_INVALID_ARGUMENT, "cast_out: dtype must be bf16 or fp16");
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("cast_out_kernel");
   return B200_OK;
 }
 

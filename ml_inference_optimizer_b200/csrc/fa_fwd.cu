@@ -633,14 +633,12 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 template <int D, typename T, bool ACCUM>
 int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t stream) {
   auto kern = fa_fwd_kernel<D, T, ACCUM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<D>::SMEM_BYTES));
-    attr_set = true;
-  }
+  static bool attr_set[64] = {};  // per device
+  B200_CUDA_OK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg<D>::SMEM_BYTES, attr_set));
   dim3 grid(p.num_pairs, p.Hq, p.B);
   kern<<<grid, NUM_THREADS, Cfg<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("fa_fwd_kernel");
   return B200_OK;
 }
 

@@ -70,6 +70,26 @@ int encode_tmap_sw128_16b(CUtensorMap* out, const void* base, int rank, const ui
 }
 
 std::atomic<int> g_sm_limit{0};
+std::atomic<int> g_group_rows{0};  // 0 = choose from the L2 budget
+std::atomic<long long> g_launches{0};
+std::atomic<const char*> g_last_gemm{""};
+
+cudaError_t set_max_dynamic_smem(const void* func, int bytes, bool (&slot)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && slot[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) slot[dev] = true;  // benign race: setting it twice is harmless
+  return e;
+}
+
+void note_launch(const char* kernel_name, bool is_gemm) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (is_gemm) g_last_gemm.store(kernel_name, std::memory_order_relaxed);
+}
+
+int gemm_group_rows() { return g_group_rows.load(std::memory_order_relaxed); }
 
 int sm_limit() { return g_sm_limit.load(std::memory_order_relaxed); }
 
@@ -98,6 +118,16 @@ int b200_set_sm_limit(int max_ctas) {
   b200::g_sm_limit.store(max_ctas, std::memory_order_relaxed);
   return B200_OK;
 }
+
+int b200_set_gemm_group_rows(int rows) {
+  if (rows != 0 && rows < 256) return b200::set_error(B200_ERR_INVALID_ARGUMENT, "raster group must cover >= 256 rows (0 = automatic)");
+  b200::g_group_rows.store(rows, std::memory_order_relaxed);
+  return B200_OK;
+}
+
+int64_t b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
+
+const char* b200_last_gemm_kernel(void) { return b200::g_last_gemm.load(std::memory_order_relaxed); }
 
 int b200_arch_ok(void) {
   int dev = 0;

@@ -41,6 +41,15 @@ int set_error(int code, const char* fmt, ...);
 int encode_tmap_sw128_16b(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                           const uint32_t* box);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a process
+// that drives several GPUs must set it on each of them. `slot` is a per-kernel static array of 64 flags.
+cudaError_t set_max_dynamic_smem(const void* func, int bytes, bool (&slot)[64]);
+
+// launch accounting (b200_launch_count / b200_last_gemm_kernel): every kernel launch of the library calls note_launch
+void note_launch(const char* kernel_name, bool is_gemm = false);
+
+int gemm_group_rows();  // b200_set_gemm_group_rows value: rows of the activation panel one L2 raster group covers
+
 int sm_count();  // multiprocessor count of the current device (cached per device)
 int sm_limit();  // b200_set_sm_limit value (0 = no limit): persistent kernels launch at most this many CTAs
 

@@ -239,5 +239,6 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
 #undef LAUNCH
 #undef LAUNCH_W
   B200_CUDA_OK(cudaGetLastError());
+  note_launch("layernorm_kernel");
   return B200_OK;
 }

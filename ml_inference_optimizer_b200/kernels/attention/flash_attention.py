@@ -255,11 +255,64 @@ class _HFAttentionAdapter(nn.Module):
     KV cache protocol (``past_key_values.update``) so ``model.generate`` works unchanged. Prefill and cached decode
     both run K1; the causal diagonal is aligned bottom-right (``causal_offset = Sk - Sq``) when a cache is present."""
 
-    def __init__(self, inner: nn.Module, layer_idx: Optional[int] = None, returns_tuple_len: int = 2):
+    def __init__(self, inner: nn.Module, layer_idx: Optional[int] = None, returns_tuple_len: int = 2, rotary: bool = False):
         super().__init__()
         self.inner = inner
         self.layer_idx = layer_idx
         self.returns_tuple_len = returns_tuple_len
+        self.rotary = rotary  # Llama family: q/k are rotated with the (cos, sin) HF passes as ``position_embeddings``
+
+    @staticmethod
+    def _apply_rotary(q, k, position_embeddings):
+        """HF ``apply_rotary_pos_emb`` for the [B,S,H,D] layout (modeling_llama.py: q*cos + rotate_half(q)*sin; the
+        reference's converter (flash_attention.py:1063-1142) replaces these modules without rotating at all)."""
+        if position_embeddings is None:
+            raise NotImplementedError("this attention module needs rotary position embeddings: the caller must pass "
+                                      "position_embeddings=(cos, sin) as HuggingFace decoder layers do")
+        cos, sin = position_embeddings
+        cos, sin = cos.unsqueeze(2).to(q.dtype), sin.unsqueeze(2).to(q.dtype)  # [B,S,1,D]
+
+        def rot(x):
+            half = x.shape[-1] // 2
+            return torch.cat((-x[..., half:], x[..., :half]), dim=-1)
+        return q * cos + rot(q) * sin, k * cos + rot(k) * sin
+
+    @staticmethod
+    def _mask_to_kv_lens(attention_mask, B: int, Sq: int, Sk: int, causal: bool):
+        """Lower HF's ``attention_mask`` to per-sequence key counts (right padding), or raise.
+
+        HF passes None (no padding, causal handled by the kernel), a 2-D ``[B,Sk]`` keep-mask, or a 4-D ``[B,1,Sq,Sk]``
+        additive / boolean mask that already contains the causal triangle. Supported: (causal +) RIGHT padding, i.e. the
+        keys a sequence keeps form a prefix. Anything else (left padding, sliding windows, prefix-LM, arbitrary masks)
+        raises NotImplementedError — never a silent unmasked run (reference convert_mask, flash_attention.py:1145-1168,
+        passes masks through to a kernel that ignores them)."""
+        if attention_mask is None:
+            return None
+        m = attention_mask
+        if m.dim() == 2:
+            keep_last = m != 0
+            keep_first = None
+        elif m.dim() == 4 and m.shape[1] == 1 and m.shape[-1] == Sk and m.shape[2] in (1, Sq):
+            vis = m if m.dtype == torch.bool else (m == 0)
+            keep_last = vis[:, 0, -1, :]   # the last query sees every kept key (causal or not)
+            keep_first = vis[:, 0, 0, :] if m.shape[2] == Sq and Sq > 1 else None
+        else:
+            raise NotImplementedError(f"attention_mask of shape {tuple(m.shape)} is not supported by the B200 attention path")
+        if keep_last.shape != (B, Sk):
+            raise NotImplementedError(f"attention_mask of shape {tuple(m.shape)} does not match keys [{B},{Sk}]")
+        lens = keep_last.sum(dim=-1).to(torch.int32)
+        idx = torch.arange(Sk, device=m.device).unsqueeze(0)
+        ok = torch.equal(keep_last, idx < lens.unsqueeze(1))
+        if ok and keep_first is not None:
+            # the first query (global position Sk - Sq) sees keys [0, Sk - Sq] under a causal mask, all kept keys otherwise
+            want = (idx <= (Sk - Sq)) & keep_last if causal else keep_last
+            ok = torch.equal(keep_first & keep_last, want)
+        if not ok:
+            raise NotImplementedError("only causal masks with RIGHT padding are supported on the B200 attention path (kept keys "
+                                      "must form a prefix; left padding / windows / arbitrary masks would need a dense-mask kernel)")
+        if bool((lens == Sk).all()):
+            return None
+        return lens.contiguous()
 
     def _qkv(self, hidden_states):
         inner = self.inner
@@ -282,12 +335,20 @@ class _HFAttentionAdapter(nn.Module):
             cache = args[0]
         B, S, _ = hidden_states.shape
         q, k, v = self._qkv(hidden_states)
+        if self.rotary:
+            pe = kwargs.get("position_embeddings")
+            if pe is None and args and isinstance(args[0], (tuple, list)) and len(args[0]) == 2:
+                pe = args[0]  # LlamaDecoderLayer passes it as a keyword; positional callers use slot 1
+            q, k = self._apply_rotary(q, k, pe)
         fa = inner.flash_attention
         orig = q.dtype
         dt = fa._compute_dtype(orig)
         if _PAGED_CONTEXT is not None:
             ctx_ = _PAGED_CONTEXT
             paged = ctx_["cache"]
+            if attention_mask is not None and self._mask_to_kv_lens(attention_mask, B, S, attention_mask.shape[-1],
+                                                                     True) is not None:
+                raise NotImplementedError("the paged prefill / decode path serves equal-length, unpadded prompts")
             if q.dtype != dt:
                 q, k, v = q.to(dt), k.to(dt), v.to(dt)
             if ctx_["mode"] == "prefill":
@@ -306,9 +367,10 @@ class _HFAttentionAdapter(nn.Module):
             k, v = k_all.transpose(1, 2), v_all.transpose(1, 2)
         if q.dtype != dt:
             q, k, v = q.to(dt), k.to(dt), v.to(dt)
-        # HF passes an additive 4-D mask; for un-padded batches it is purely causal, which the kernel does itself
+        # HF passes an additive 4-D mask: causal triangle (the kernel does that itself) + padding (lowered to kv_lens)
+        kv_lens = self._mask_to_kv_lens(attention_mask, B, S, k.shape[1], inner.config.causal)
         ctx = ops.flash_attn_fwd(q, k, v, causal=inner.config.causal, softmax_scale=inner.config.softmax_scale,
-                                 causal_offset=k.shape[1] - S)
+                                 causal_offset=k.shape[1] - S, kv_lens=kv_lens)
         out = inner.o_proj(ctx.reshape(B, S, inner.hidden_size).to(orig))
         return (out,) + (None,) * (self.returns_tuple_len - 1)
 
@@ -379,12 +441,15 @@ class ModelConverter:
             for dst, src in ((new.q_proj, m.q_proj), (new.k_proj, m.k_proj), (new.v_proj, m.v_proj), (new.o_proj, o_src)):
                 self._copy_linear(dst, src.weight, src.bias)
             if hasattr(m, "layer_idx") and type(m).__module__.startswith("transformers."):
-                if hasattr(m, "rotary_emb") or "rotary" in "".join(n for n, _ in m.named_modules()).lower() or \
-                        "Llama" in cls or "Mistral" in cls or "Qwen" in cls:
-                    raise NotImplementedError(f"{cls} applies rotary position embeddings inside the attention module; "
-                                              "rotary is outside this hot path (use FlashAttention3 on rotated q/k)")
+                for extra in ("q_norm", "k_norm", "sliding_window"):
+                    if getattr(m, extra, None) is not None:
+                        raise NotImplementedError(f"{cls}.{extra} is not supported by the B200 attention replacement")
+                scaling = getattr(m, "scaling", None)
+                if scaling is not None and abs(float(scaling) - head_dim ** -0.5) > 1e-9:
+                    new.config.softmax_scale = float(scaling)
+                rotary = hasattr(m, "rotary_emb") or any(t in cls for t in ("Llama", "Mistral", "Qwen2"))
                 new.to(device=ref_param.device, dtype=ref_param.dtype)
-                return _HFAttentionAdapter(new, layer_idx=m.layer_idx, returns_tuple_len=2)
+                return _HFAttentionAdapter(new, layer_idx=m.layer_idx, returns_tuple_len=2, rotary=rotary)
         else:
             src = m.qkv_proj if hasattr(m, "qkv_proj") else m.qkv
             head_dim = hidden // heads

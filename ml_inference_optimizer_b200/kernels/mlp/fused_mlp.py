@@ -17,7 +17,50 @@ import torch.nn as nn
 from ... import ops
 
 __all__ = ["FusedMLPConfig", "FusedMLP", "FusedMLPGeluTanh", "FusedMLPSwiGLU", "FusedMLPReLU", "FusedTransformerMLP",
-           "MLPConverter"]
+           "MLPConverter", "resolve_activation"]
+
+
+def resolve_activation(fn) -> str:
+    """Strict map from an activation (string, function, ``nn.Module`` or HF activation object) to a fused epilogue:
+    ``"gelu_tanh"``, ``"gelu_erf"``, ``"relu"`` or ``"silu"`` (the gate activation of SwiGLU). Anything without a fused
+    epilogue (QuickGELU, plain Tanh, Mish, GeGLU gates ...) raises instead of being approximated — a converted model must
+    compute what the original computed. (The reference maps by substring, fused_mlp.py:440-470.)"""
+    import functools
+    import torch.nn.functional as F
+
+    if fn is None:
+        raise ValueError("the MLP block has no activation attribute (act_fn / activation_fn / act / activation)")
+    if isinstance(fn, functools.partial):
+        if fn.func is F.gelu:
+            return "gelu_tanh" if fn.keywords.get("approximate") == "tanh" else "gelu_erf"
+        fn = fn.func
+    if isinstance(fn, str):
+        key = fn.lower()
+        table = {"gelu_new": "gelu_tanh", "gelu_tanh": "gelu_tanh", "gelu_pytorch_tanh": "gelu_tanh", "gelu_fast": "gelu_tanh",
+                 "gelu": "gelu_erf", "gelu_erf": "gelu_erf", "gelu_python": "gelu_erf", "relu": "relu", "silu": "silu",
+                 "swish": "silu", "swiglu": "silu"}
+        if key in table:
+            return table[key]
+        raise ValueError(f"activation {fn!r} has no fused epilogue (supported: gelu, gelu_new/gelu_tanh, relu, silu)")
+    if isinstance(fn, nn.GELU):
+        return "gelu_tanh" if fn.approximate == "tanh" else "gelu_erf"
+    if isinstance(fn, nn.ReLU) or fn is F.relu or fn is torch.relu:
+        return "relu"
+    if isinstance(fn, nn.SiLU) or fn is F.silu:
+        return "silu"
+    if fn is F.gelu:
+        return "gelu_erf"
+    name = (getattr(fn, "__name__", None) or type(fn).__name__).lower()
+    by_class = {"newgeluactivation": "gelu_tanh", "pytorchgelutanh": "gelu_tanh", "gelutanh": "gelu_tanh",
+                "fastgeluactivation": "gelu_tanh",  # 0.5x(1+tanh(0.79788456x(1+0.044715x^2))): the same function
+                "geluactivation": "gelu_erf", "reluactivation": "relu", "siluactivation": "silu", "gelu_new": "gelu_tanh",
+                "gelu": "gelu_erf", "relu": "relu", "silu": "silu", "swish": "silu"}
+    if name in by_class:
+        if name == "geluactivation" and getattr(fn, "act", None) is not None and getattr(fn.act, "__name__", "") == "_gelu_python":
+            return "gelu_erf"
+        return by_class[name]
+    raise ValueError(f"activation {fn!r} has no fused epilogue (supported: exact / tanh GELU, ReLU, SiLU gates); "
+                     "refusing to convert rather than computing something else")
 
 
 @dataclass
@@ -57,6 +100,8 @@ class FusedMLP(nn.Module):
         act = self.config.activation_fn
         if act == "gelu":
             return "gelu_erf"  # exact GELU for the bare module, fused_mlp.py:162-163
+        if act in ("gelu_erf", "gelu_exact"):
+            return "gelu_erf"
         if act in ("gelu_tanh", "gelu_new", "gelu_pytorch_tanh"):
             return "gelu_tanh"
         if act == "relu":
@@ -167,26 +212,47 @@ class MLPConverter:
         self.activation_map = {"gelu": "gelu", "relu": "relu", "silu": "silu", "swish": "silu", "swiglu": "swiglu",
                                "gelu_new": "gelu"}
 
+    @staticmethod
+    def _module_activation(module: nn.Module):
+        for attr in ("act_fn", "activation_fn", "act", "activation"):
+            if getattr(module, attr, None) is not None:
+                return getattr(module, attr)
+        cfg = getattr(module, "config", None)
+        for attr in ("hidden_act", "activation_function"):
+            if cfg is not None and getattr(cfg, attr, None) is not None:
+                return getattr(cfg, attr)
+        return None
+
     def _detect_mlp_type(self, module: nn.Module) -> Optional[Dict[str, Any]]:
+        """Structure decides the kind; the activation is RESOLVED from the module (``resolve_activation``), never guessed:
+        a block whose activation has no fused epilogue raises."""
         cls = type(module).__name__
         if isinstance(module, (FusedMLP, FusedTransformerMLP, _MLPAdapter)):
             return None
+        # FusedTransformerMLP spelling: "gelu" = tanh GELU (reference :340-341), "gelu_erf" = exact
+        spell = {"gelu_tanh": "gelu", "gelu_erf": "gelu_erf", "relu": "relu"}
+
+        def plain(kind, hidden, inter, default=None):
+            act = self._module_activation(module)
+            name = resolve_activation(act if act is not None else default)
+            if name not in spell:
+                raise ValueError(f"{cls}: activation {name!r} has no fused epilogue for an un-gated MLP")
+            return {"kind": kind, "hidden": hidden, "intermediate": inter, "activation": spell[name]}
+
         if hasattr(module, "c_fc") and hasattr(module, "c_proj") and "mlp" in cls.lower():
             w = module.c_fc.weight  # Conv1D: [in, out]
-            act = type(getattr(module, "act", None)).__name__
-            return {"kind": "gpt2", "hidden": w.shape[0], "intermediate": w.shape[1],
-                    "activation": "relu" if "relu" in act.lower() else "gelu"}
+            return plain("gpt2", w.shape[0], w.shape[1])
         if all(hasattr(module, a) for a in ("gate_proj", "up_proj", "down_proj")):
+            gate_act = resolve_activation(self._module_activation(module))
+            if gate_act != "silu":
+                raise ValueError(f"{cls}: gated MLP with a {gate_act} gate (GeGLU-style) has no fused epilogue; only SiLU gates "
+                                 "(SwiGLU) are fused")
             return {"kind": "llama", "hidden": module.up_proj.in_features, "intermediate": module.up_proj.out_features,
                     "activation": "swiglu"}
         if hasattr(module, "fc1") and hasattr(module, "fc2") and isinstance(module.fc1, nn.Linear) and "mlp" in cls.lower():
-            act = getattr(module, "activation_fn", getattr(module, "act", None))
-            name = getattr(act, "__name__", type(act).__name__).lower()
-            return {"kind": "fc", "hidden": module.fc1.in_features, "intermediate": module.fc1.out_features,
-                    "activation": "relu" if "relu" in name else "gelu"}
+            return plain("fc", module.fc1.in_features, module.fc1.out_features)
         if hasattr(module, "dense_h_to_4h") and hasattr(module, "dense_4h_to_h"):
-            return {"kind": "megatron", "hidden": module.dense_h_to_4h.in_features,
-                    "intermediate": module.dense_h_to_4h.out_features, "activation": "gelu"}
+            return plain("megatron", module.dense_h_to_4h.in_features, module.dense_h_to_4h.out_features, default="gelu")
         return None
 
     @staticmethod

@@ -429,6 +429,21 @@ def set_sm_limit(max_ctas: int) -> None:
     check("b200_set_sm_limit", _lib.load().b200_set_sm_limit(int(max_ctas)))
 
 
+def set_gemm_group_rows(rows: int) -> None:
+    """Rows of the activation panel one L2 raster group of the persistent GEMMs covers; see ``b200_set_gemm_group_rows``."""
+    check("b200_set_gemm_group_rows", _lib.load().b200_set_gemm_group_rows(int(rows)))
+
+
+def launch_count() -> int:
+    """Kernel launches issued by the library in this process so far (``b200_launch_count``)."""
+    return int(_lib.load().b200_launch_count())
+
+
+def last_gemm_kernel() -> str:
+    """Name of the GEMM kernel the last linear / FusedMLP call dispatched to."""
+    return (_lib.load().b200_last_gemm_kernel() or b"").decode()
+
+
 def sm_count(device=None) -> int:
     return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
 

@@ -118,6 +118,8 @@ def ring_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, ca
     if partition not in ("contiguous", "zigzag"):
         raise ValueError(f"unknown partition {partition!r}")
     backend = backend or CudaRingBackend()
+    # group=None means the WORLD group (as in torch.distributed). Callers with "no sequence-parallel group" must not get
+    # here: SequenceParallelAttention routes sp_size == 1 to the local kernel.
     n = get_world_size(group) if dist.is_initialized() else 1
     r = get_rank(group) if dist.is_initialized() else 0
     B, S, Hq, D = q.shape

@@ -132,12 +132,18 @@ class SequenceParallelAttention(nn.Module):
         return o.transpose(1, 2)
 
     def _ring_attention(self, q, k, v, attention_mask=None):
+        if self.config.sp_size == 1:
+            # no SP group: get_sp_group() is None, which the ring would read as WORLD and circulate K/V through the
+            # data-parallel replicas, mixing unrelated batches. One rank's sequence is the whole sequence.
+            return self._local_attention(q, k, v, attention_mask)
         o = ring_attention_forward(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=self.causal,
                                    group=self.sp_group, partition=self.partition, backend=self.backend,
                                    overlap=self.config.overlap_communication)
         return o.transpose(1, 2)
 
     def _full_attention(self, q, k, v, attention_mask=None):
+        if self.config.sp_size == 1:
+            return self._local_attention(q, k, v, attention_mask)
         kf = comm.gather_along_sequence_dim(k.transpose(1, 2).contiguous(), self.config.sp_size, self.partition, self.sp_group)
         vf = comm.gather_along_sequence_dim(v.transpose(1, 2).contiguous(), self.config.sp_size, self.partition, self.sp_group)
         if self.causal:

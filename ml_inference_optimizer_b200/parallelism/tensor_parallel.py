@@ -11,6 +11,7 @@ weights (:684-690), the ``num_partitions`` keyword mismatch (:293).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -26,23 +27,11 @@ __all__ = ["TensorParallelConfig", "ColumnParallelLinear", "RowParallelLinear", 
 
 
 def activation_name(fn) -> str:
-    """Map the reference's activation callables (``F.gelu`` default, :336) to the fused-epilogue selector."""
-    if isinstance(fn, str):
-        return fn
-    name = getattr(fn, "__name__", type(fn).__name__).lower()
-    if getattr(fn, "keywords", None) and fn.keywords.get("approximate") == "tanh":
-        return "gelu_tanh"
-    if isinstance(fn, nn.GELU):
-        return "gelu_tanh" if fn.approximate == "tanh" else "gelu_erf"
-    if "gelu_new" in name or "newgelu" in name or "gelu_tanh" in name:
-        return "gelu_tanh"
-    if "gelu" in name:
-        return "gelu_erf"
-    if "relu" in name:
-        return "relu"
-    if "silu" in name or "swish" in name or "swiglu" in name:
-        return "swiglu"
-    raise ValueError(f"activation {fn!r} has no fused epilogue (supported: gelu, gelu_tanh, relu, silu/swiglu)")
+    """Map the reference's activation callables (``F.gelu`` default, :336) to the fused-epilogue selector — strictly
+    (``kernels.mlp.fused_mlp.resolve_activation``): an activation without a fused epilogue raises."""
+    from ..kernels.mlp.fused_mlp import resolve_activation
+    name = resolve_activation(fn)
+    return "swiglu" if name == "silu" else name
 
 
 class TensorParallelConfig:
@@ -178,6 +167,14 @@ class TensorParallelMLP(nn.Module):
         self.overlap_chunks = 4
         self.overlap_min_tokens = 8192
         self.comm_sms = 32  # SMs left free for the collective while chunks are in flight (measured at tp=8: 2.02 -> 1.90 ms)
+        # "auto": K6 over symmetric memory when it can be set up, else NCCL; "symmetric": K6 or raise; "nccl": NCCL only
+        self.reduce_impl = os.environ.get("B200_TP_REDUCE", "auto")
+        self.comm_ctas = int(os.environ.get("B200_TP_COMM_CTAS", "16"))          # CTAs of K6 next to running GEMMs
+        self.comm_ctas_single = int(os.environ.get("B200_TP_COMM_CTAS_SINGLE", "48"))  # ... when nothing else runs
+        # "copy": return a fresh tensor (safe default). "view": return the rows inside the symmetric buffer — valid
+        # until the second-next TensorParallelMLP call on this group (two buffers rotate); saves one pass over [T, h].
+        self.symmetric_output = "copy"
+        self.last_reduce = "nccl"
 
     @classmethod
     def from_dense(cls, w_up, b_up, w_down, b_down, config: TensorParallelConfig, activation: Callable = F.gelu,
@@ -202,13 +199,82 @@ class TensorParallelMLP(nn.Module):
             lead = hidden_states.shape[:-1]
             x2 = hidden_states.reshape(-1, hidden_states.shape[-1])
             T = x2.shape[0]
-            if self.config.tp_size > 1 and self.overlap_chunks > 1 and T >= self.overlap_min_tokens and dist.is_initialized():
-                return self._forward_overlapped(x2, act, gw, gb).reshape(*lead, -1)
+            if self.config.tp_size > 1 and dist.is_initialized() and x2.is_cuda:
+                if self.reduce_impl in ("auto", "symmetric") and T > 0:
+                    pool = self._symmetric_pool(T * down.out_features * x2.element_size(), x2.device)
+                    if pool is not None:
+                        return self._forward_symmetric(x2, act, gw, gb, pool).reshape(*lead, -1)
+                if self.overlap_chunks > 1 and T >= self.overlap_min_tokens:
+                    return self._forward_overlapped(x2, act, gw, gb).reshape(*lead, -1)
             # the down bias must be added once, after the reduction (reference :304-308)
             partial = ops.fused_mlp(hidden_states, up.weight, up.bias, down.weight, None, act, gw, gb)
         if self.config.tp_size > 1:
             comm.all_reduce(partial, group=self.config.get_tp_group())
         return partial if down.bias is None else partial + down.bias
+
+    # ---- symmetric-memory path: K3 writes its partial rows into a peer-mapped buffer, K6 reduces them in the switch ----
+    _POOLS: dict = {}
+
+    def _symmetric_pool(self, nbytes: int, device):
+        """Two rotating symmetric buffers shared by every TensorParallelMLP of the group (created collectively on first
+        use, grown when a larger input arrives). None if symmetric memory cannot be set up (then NCCL reduces)."""
+        from .symmetric import SymmetricBuffer, symmetric_available
+        group = self.config.get_tp_group()
+        key = (id(group), device.index)
+        entry = TensorParallelMLP._POOLS.get(key)
+        if entry is not None and entry["failed"]:
+            if self.reduce_impl == "symmetric":
+                raise RuntimeError(f"symmetric memory is not available: {entry['failed']}")
+            return None
+        if entry is None or entry["nbytes"] < nbytes:
+            try:
+                if not symmetric_available():
+                    raise RuntimeError("torch.distributed._symmetric_memory is not importable")
+                bufs = [SymmetricBuffer(nbytes, group, device) for _ in range(2)]
+                entry = {"nbytes": nbytes, "bufs": bufs, "turn": 0, "failed": None, "stream": torch.cuda.Stream(device, priority=-1)}
+            except Exception as e:  # noqa: BLE001 - no fabric / IPC support: the NCCL path stays correct
+                entry = {"nbytes": 0, "bufs": [], "turn": 0, "failed": f"{type(e).__name__}: {e}", "stream": None}
+                TensorParallelMLP._POOLS[key] = entry
+                if self.reduce_impl == "symmetric":
+                    raise
+                return None
+            TensorParallelMLP._POOLS[key] = entry
+        return entry
+
+    def _forward_symmetric(self, x2: torch.Tensor, act: str, gw, gb, pool) -> torch.Tensor:
+        """Token-chunked pipeline on two streams: the GEMMs of chunk c+1 (K3, on all SMs but ``comm_ctas``) run while K6
+        reduces chunk c through the NVSwitch (multimem.ld_reduce / multimem.st; bias fused). Same arithmetic as one fused
+        call + one all-reduce + bias, with the partial sums accumulated in fp32 inside the switch."""
+        from .. import ops
+        up, down = self.dense_h_to_4h, self.dense_4h_to_h
+        T, h_out = x2.shape[0], down.out_features
+        buf = pool["bufs"][pool["turn"]]
+        pool["turn"] ^= 1
+        out = buf.view((T, h_out), x2.dtype)
+        main = torch.cuda.current_stream(x2.device)
+        side = pool["stream"]
+        n = self.overlap_chunks if T >= self.overlap_min_tokens else 1
+        rows = ((T + n - 1) // n + 255) // 256 * 256
+        bias = down.bias
+        if n > 1:
+            ops.set_sm_limit(max(2, ops.sm_count(x2.device) - self.comm_ctas))
+        try:
+            for r0 in range(0, T, rows):
+                r1 = min(T, r0 + rows)
+                ops.fused_mlp(x2[r0:r1], up.weight, up.bias, down.weight, None, act, gw, gb, out=out[r0:r1])
+                if n > 1:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        buf.all_reduce_(out[r0:r1], bias, max_ctas=self.comm_ctas)
+                else:
+                    buf.all_reduce_(out[r0:r1], bias, max_ctas=self.comm_ctas_single)
+        finally:
+            if n > 1:
+                ops.set_sm_limit(0)
+        if n > 1:
+            main.wait_stream(side)
+        self.last_reduce = "symmetric-multicast" if buf.multicast else "symmetric-peer"
+        return out if self.symmetric_output == "view" else out.clone()
 
     def _forward_overlapped(self, x2: torch.Tensor, act: str, gw, gb) -> torch.Tensor:
         """Token-chunked pipeline: while NCCL reduces chunk c (on its own high-priority stream, using the SMs the GEMMs
@@ -301,6 +367,9 @@ class ModelParallelConverter:
         if isinstance(m, (TensorParallelMLP, ColumnParallelLinear, RowParallelLinear)):
             return None
         if all(hasattr(m, a) for a in ("gate_proj", "up_proj", "down_proj")):
+            from ..kernels.mlp.fused_mlp import MLPConverter, resolve_activation
+            if resolve_activation(MLPConverter._module_activation(m)) != "silu":
+                raise ValueError(f"{type(m).__name__}: only SiLU-gated (SwiGLU) MLPs have a fused tensor-parallel epilogue")
             return TensorParallelMLP.from_dense(m.up_proj.weight, m.up_proj.bias, m.down_proj.weight, m.down_proj.bias,
                                                 self.config, F.silu, m.gate_proj.weight, m.gate_proj.bias)
         if hasattr(m, "fc1") and hasattr(m, "fc2") and isinstance(m.fc1, nn.Linear):

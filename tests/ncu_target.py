@@ -16,8 +16,8 @@ if what in ("fa", "fa64"):
     q, k, v = (torch.randn(B, S, H, D, device="cuda", dtype=bf) for _ in range(3))
     for _ in range(reps):
         ops.flash_attn_fwd(q, k, v, causal=True)
-elif what in ("gemm1", "gemm2", "mlp"):
-    T, h, i = 32768, 4096, 11008
+elif what in ("gemm1", "gemm2", "mlp", "mlp_c2"):
+    T, h, i = (32768, 4096, 11008) if what != "mlp_c2" else (32768, 768, 3072)
     x = torch.randn(T, h, device="cuda", dtype=bf)
     wu, wg = (torch.randn(i, h, device="cuda", dtype=bf) * 0.02 for _ in range(2))
     wd = torch.randn(h, i, device="cuda", dtype=bf) * 0.02
@@ -27,6 +27,8 @@ elif what in ("gemm1", "gemm2", "mlp"):
             ops.linear_act(x, wu, None, "swiglu", wg, None)
         elif what == "gemm2":
             ops.linear_act(hmid, wd, None, None)
+        elif what == "mlp_c2":
+            ops.fused_mlp(x, wu, None, wd, None, "gelu_tanh")
         else:
             ops.fused_mlp(x, wu, None, wd, None, "swiglu", wg, None)
 elif what in ("decode", "decode_gqa"):

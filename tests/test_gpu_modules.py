@@ -187,6 +187,74 @@ def test_optimizer_on_hf_gpt2_matches_eager_and_generates():
         (full.float().topk(2).values[0, 0] - full.float().topk(2).values[0, 1]).item() < 5e-2
 
 
+def test_optimizer_on_hf_llama_matches_eager():
+    """configs[2-3] name the Llama family: ``Optimizer.optimize`` on an HF Llama (random init, 2 layers, GQA 8q/2kv, rotary
+    applied inside the attention replacement) must reproduce the eager model's logits, prefill and cached decode."""
+    import copy
+
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from ml_inference_optimizer import Optimizer
+
+    torch.manual_seed(0)
+    cfg = LlamaConfig(hidden_size=512, intermediate_size=1408, num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=2,
+                      vocab_size=1024, max_position_embeddings=512, attn_implementation="eager")
+    eager = LlamaForCausalLM(cfg).eval()
+    ids = torch.randint(0, cfg.vocab_size, (2, 160))
+    with torch.no_grad():
+        ref = eager(ids).logits
+    model = copy.deepcopy(eager).to("cuda", torch.bfloat16)
+    opt = Optimizer(model)
+    optimized = opt.optimize(use_flash_attention=True, use_fused_mlp=True, tensor_parallel_size=1)
+    assert opt.applied == {"flash_attention": True, "fused_mlp": True}
+    with torch.no_grad():
+        got = optimized(ids.cuda()).logits
+    err = (got.float().cpu() - ref).abs().max().item()
+    assert err < 5e-2, err
+    out = optimized.generate(input_ids=ids[:1, :48].cuda(), max_new_tokens=6, do_sample=False)
+    assert out.shape == (1, 54)
+    with torch.no_grad():
+        full = optimized(out[:, :-1]).logits[:, -1].float()
+    top = full.topk(2).values[0]
+    assert full.argmax(-1).item() == out[0, -1].item() or (top[0] - top[1]).item() < 5e-2
+
+
+def test_hf_adapter_right_padded_batch_and_unsupported_masks():
+    """the HF adapter must honour ``attention_mask``. A right-padded batch through the converted GPT-2 equals
+    the eager model on the valid positions; left padding raises instead of silently attending to pad tokens."""
+    import copy
+
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from ml_inference_optimizer import Optimizer
+
+    torch.manual_seed(1)
+    cfg = GPT2Config(n_layer=2, attn_implementation="eager")
+    eager = GPT2LMHeadModel(cfg).eval()
+    ids = torch.randint(0, cfg.vocab_size, (3, 96))
+    lens = [96, 40, 71]
+    mask = torch.zeros(3, 96, dtype=torch.long)
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    with torch.no_grad():
+        ref = eager(ids, attention_mask=mask).logits
+    model = copy.deepcopy(eager).to("cuda", torch.bfloat16)
+    optimized = Optimizer(model).optimize(use_flash_attention=True, use_fused_mlp=True)
+    with torch.no_grad():
+        got = optimized(ids.cuda(), attention_mask=mask.cuda()).logits.float().cpu()
+    for b, n in enumerate(lens):
+        assert (got[b, :n] - ref[b, :n]).abs().max().item() < 5e-2
+    # the padded keys really are masked: changing the pad tokens does not change the valid positions at all
+    ids2 = ids.clone()
+    ids2[1, 40:] = 7
+    with torch.no_grad():
+        got2 = optimized(ids2.cuda(), attention_mask=mask.cuda()).logits.float().cpu()
+    assert torch.equal(got2[1, :40], got[1, :40])
+    left = torch.flip(mask, dims=[1])
+    with pytest.raises(NotImplementedError):
+        optimized(ids.cuda(), attention_mask=left.cuda())
+
+
 def test_paged_generation_matches_cached_generation():
     """Row f1: prefill -> KV append -> paged decode attention through the block tables reproduces what the same model
     generates with the HF (contiguous) cache, and the runner reports the reference's metric keys."""

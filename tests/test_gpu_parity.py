@@ -329,6 +329,55 @@ def test_fused_mlp_vs_oracle(ops, T, h, i, act, bias):
     check_out(y, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=1e-2)
 
 
+FUSED_LAUNCH_CASES = [
+    # T, h, i, act, bias — prefill-sized (T >= 1024): one launch, up(+gate) and down projection interleaved by row groups
+    (1024, 512, 1408, "swiglu", True),
+    (1500, 768, 3072, "gelu_tanh", True),      # ragged last row-block, GPT-2 widths (intermediate L2-resident mode)
+    (4096 + 77, 512, 1376, "swiglu", False),   # the tensor-parallel shard width of C3 at tp=8, ragged T, bias-less
+    (2048, 1024, 4096, "relu", True),
+    (8192, 768, 3072, "gelu", True),           # several row groups: P1 -> P2 dependency counters cross group boundaries
+    (2304, 264, 520, "swiglu", True),          # nothing a multiple of the tile
+]
+
+
+@pytest.mark.parametrize("T,h,i,act,bias", FUSED_LAUNCH_CASES)
+def test_fused_mlp_single_launch_vs_oracle_and_two_launch(ops, T, h, i, act, bias, monkeypatch):
+    """Row a6: fused_mlp_pair_kernel (ONE launch; the bf16 intermediate is handed from the up to the down projection
+    through per-row-block counters) against the oracle, and bit-identical to the two-launch path on the same tiles."""
+    x, wu, bu, wd, bd, wg, bg = make_mlp(T, h, i, act, bias=bias)
+    monkeypatch.setenv("B200_MLP_FUSED", "1")
+    y = ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg)
+    assert ops.last_gemm_kernel().startswith("fused_mlp_pair_kernel")
+    for g, lag in ((1, 1), (2, 3), (3, 1)):   # stress the tile list: tiny groups, long and short P1 -> P2 lags
+        monkeypatch.setenv("B200_FUSED_G", str(g)); monkeypatch.setenv("B200_FUSED_LAG", str(lag))
+        assert torch.equal(ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg), y), f"group {g} lag {lag} changes the result"
+    monkeypatch.setenv("B200_FUSED_G", "0"); monkeypatch.setenv("B200_FUSED_LAG", "0")
+    monkeypatch.setenv("B200_MLP_FUSED", "0")
+    y2 = ops.fused_mlp(x, wu, bu, wd, bd, act, wg, bg)
+    two = ops.last_gemm_kernel()
+    assert not two.startswith("fused_mlp")
+    if two.startswith("gemm_act_pair_kernel"):   # same 256x256 tiles, same k order: bit-identical
+        assert torch.equal(y, y2)
+    c = lambda t: None if t is None else t.cpu()
+    ref = orc.mlp_ref(c(x), c(wu), c(bu), c(wd), c(bd), act, c(wg), c(bg))
+    check_out(y, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=1e-2)
+
+
+def test_fused_mlp_single_launch_repeated_calls_and_streams(ops, monkeypatch):
+    """The dependency counters live in the caller's workspace and are re-zeroed per launch: back-to-back calls (same
+    workspace) and a call on a side stream must all give the same bits."""
+    monkeypatch.setenv("B200_MLP_FUSED", "1")
+    x, wu, bu, wd, bd, wg, bg = make_mlp(3000, 512, 1024, "swiglu", bias=True)
+    ys = [ops.fused_mlp(x, wu, bu, wd, bd, "swiglu", wg, bg) for _ in range(5)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ys.append(ops.fused_mlp(x, wu, bu, wd, bd, "swiglu", wg, bg))
+    torch.cuda.synchronize()
+    for y in ys[1:]:
+        assert torch.equal(y, ys[0])
+
+
 @pytest.mark.parametrize("act", [None, "gelu_tanh", "gelu", "relu", "swiglu"])
 def test_linear_act_vs_oracle(ops, act):
     T, K, N = 300, 768, 1024

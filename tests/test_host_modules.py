@@ -107,6 +107,96 @@ def test_activation_mapping():
         activation_name(torch.tanh)
 
 
+def test_activation_resolution_is_strict():
+    """converters resolve the activation from the module and refuse what has no fused epilogue (the reference
+    maps by substring, fused_mlp.py:440-470): QuickGELU / Tanh / GeGLU must raise, exact vs tanh GELU stay distinct."""
+    from transformers.activations import ACT2FN
+
+    from ml_inference_optimizer_b200.kernels.mlp.fused_mlp import resolve_activation
+    from ml_inference_optimizer_b200.parallelism.tensor_parallel import ModelParallelConverter, TensorParallelConfig
+
+    assert resolve_activation(ACT2FN["gelu_new"]) == "gelu_tanh" and resolve_activation(ACT2FN["gelu"]) == "gelu_erf"
+    assert resolve_activation(ACT2FN["gelu_pytorch_tanh"]) == "gelu_tanh" and resolve_activation(ACT2FN["silu"]) == "silu"
+    assert resolve_activation("gelu_new") == "gelu_tanh" and resolve_activation(nn.GELU()) == "gelu_erf"
+    for bad in (ACT2FN["quick_gelu"], ACT2FN["tanh"], nn.Mish(), torch.tanh, "mish", None):
+        with pytest.raises(ValueError):
+            resolve_activation(bad)
+
+    class FcMLP(nn.Module):
+        def __init__(self, act):
+            super().__init__()
+            self.fc1, self.fc2, self.activation_fn = nn.Linear(16, 32), nn.Linear(32, 16), act
+
+    class Gated(nn.Module):
+        def __init__(self, act):
+            super().__init__()
+            self.gate_proj, self.up_proj, self.down_proj = nn.Linear(16, 32), nn.Linear(16, 32), nn.Linear(32, 16)
+            self.act_fn = act
+
+    class Holder(nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.mlp = m
+
+    h = Holder(FcMLP(nn.GELU()))                       # exact GELU stays exact
+    MLPConverter().convert_model(h)
+    assert h.mlp.inner.mlp._activation() == "gelu_erf"
+    h = Holder(FcMLP(ACT2FN["gelu_new"]))
+    MLPConverter().convert_model(h)
+    assert h.mlp.inner.mlp._activation() == "gelu_tanh"
+    for bad in (FcMLP(ACT2FN["quick_gelu"]), FcMLP(nn.SiLU()), FcMLP(nn.Tanh()), Gated(nn.GELU(approximate="tanh"))):
+        with pytest.raises(ValueError):                 # SiLU without a gate, QuickGELU, Tanh, GeGLU: no fused epilogue
+            MLPConverter().convert_model(Holder(bad))
+    with pytest.raises(ValueError):
+        ModelParallelConverter(TensorParallelConfig()).convert_model(Holder(Gated(nn.GELU())))
+
+
+def test_hf_mask_lowering_to_kv_lens():
+    """HF's 2-D keep mask / 4-D additive causal+padding mask -> per-sequence key counts; left padding, windows and
+    non-causal structure raise (never a silent unmasked run)."""
+    from ml_inference_optimizer_b200.kernels.attention.flash_attention import _HFAttentionAdapter as A
+
+    B, S = 2, 6
+    keep = torch.tensor([[1, 1, 1, 1, 0, 0], [1, 1, 1, 1, 1, 1]])
+    assert A._mask_to_kv_lens(keep, B, S, S, True).tolist() == [4, 6]
+    assert A._mask_to_kv_lens(torch.ones(B, S), B, S, S, True) is None      # no padding: nothing to mask
+    causal = torch.tril(torch.ones(S, S, dtype=torch.bool))
+    vis = causal[None, None] & keep.bool()[:, None, None, :]
+    additive = torch.zeros(B, 1, S, S).masked_fill(~vis, torch.finfo(torch.float32).min)
+    assert A._mask_to_kv_lens(additive, B, S, S, True).tolist() == [4, 6]
+    assert A._mask_to_kv_lens(vis, B, S, S, True).tolist() == [4, 6]
+    # cached decode: one query row against Sk keys
+    assert A._mask_to_kv_lens(additive[:, :, -1:, :], B, 1, S, True).tolist() == [4, 6]
+    with pytest.raises(NotImplementedError):                                   # left padding
+        A._mask_to_kv_lens(torch.flip(keep, dims=[1]), B, S, S, True)
+    window = vis & ~torch.tril(torch.ones(S, S, dtype=torch.bool), -3)[None, None]
+    with pytest.raises(NotImplementedError):                                   # sliding window hides early keys
+        A._mask_to_kv_lens(window, B, S, S, True)
+    with pytest.raises(NotImplementedError):                                   # bidirectional mask on a causal module
+        A._mask_to_kv_lens(torch.ones(B, 1, S, S, dtype=torch.bool), B, S, S, True)
+    with pytest.raises(NotImplementedError):
+        A._mask_to_kv_lens(torch.ones(B, 3, S, S), B, S, S, True)
+
+
+def test_sequence_parallel_without_sp_group_stays_local():
+    """sp_size == 1 has no SP group; ring / full handling must run the local kernel, not a ring over WORLD."""
+    from ml_inference_optimizer_b200.parallelism.sequence_parallel import SequenceParallelAttention, SequenceParallelConfig
+
+    calls = []
+
+    class Backend:
+        def attn(self, q, k, v, causal, scale):
+            calls.append("attn")
+            return torch.zeros_like(q), torch.zeros(q.shape[0], q.shape[2], q.shape[1])
+
+    for handling in ("ring", "full", "local"):
+        m = SequenceParallelAttention(32, 4, SequenceParallelConfig(world_size=1, sp_size=1, attention_handling=handling),
+                                      attention_dropout=0.0)
+        m.backend = Backend()
+        m(torch.randn(1, 8, 32))
+    assert calls == ["attn"] * 3
+
+
 def test_converters_copy_weights_gpt2():
     from transformers import GPT2Config, GPT2LMHeadModel
 
@@ -133,6 +223,7 @@ def test_mlp_converter_llama_style_and_load_from_standard():
             super().__init__()
             self.gate_proj, self.up_proj = nn.Linear(32, 96, bias=False), nn.Linear(32, 96, bias=False)
             self.down_proj = nn.Linear(96, 32, bias=False)
+            self.act_fn = nn.SiLU()
 
     class Block(nn.Module):
         def __init__(self):
