@@ -25,13 +25,14 @@ def test_header_symbols_are_exported(built_lib):
 def test_header_cites_reference_interfaces():
     header = open(os.path.join(ROOT, "include", "b200_attn_mlp.h")).read()
     for cite in ("flash_attention_kernels.py:1150", "attention_kernels.py:1206", "attention_kernels.py:1314",
-                 "mlp_kernels.py:648", "tensor_parallel.py:173"):
+                 "mlp_kernels.py:648", "tensor_parallel.py:173", "tensor_parallel.py:296-308"):
         assert cite in header
 
 
 def test_version_and_pure_host_queries(built_lib):
     assert b"sm_100a" in built_lib.b200_version()
-    assert built_lib.b200_fused_mlp_workspace_bytes(32768, 4096, 11008) == 32768 * 11008 * 2  # wide problem: no split-K
+    # wide problem: no split-K; the intermediate + the single-launch kernel's counters (2 per 256-row block + 1, 256-aligned)
+    assert built_lib.b200_fused_mlp_workspace_bytes(32768, 4096, 11008) == 32768 * 11008 * 2 + 1280
     assert built_lib.b200_linear_act_workspace_bytes(32768, 4096, 11008, 4) == 0
     assert built_lib.b200_fa_decode_workspace_bytes(4, 32, 8, 128, 8192, 1) == 0
     assert built_lib.b200_fa_decode_workspace_bytes(4, 32, 8, 128, 8192, 4) == 4 * 32 * 4 * 129 * 4
