@@ -193,6 +193,23 @@ int b200_layernorm(const void* x, const void* residual, const void* weight, cons
                    int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps, float residual_alpha, int dtype,
                    void* stream);
 
+/* ---- K1 over the paged cache: short-q / chunked-prefill attention (q_len > 1) --------------------------
+ * Replaces triton_paged_attention_forward for q_seq_len > 1 (kernels/triton/attention_kernels.py:1206-1311, which picks
+ * BLOCK_SIZE_M = 64 for it, :1251) and FlashAttentionLayer's paged branch (kernels/attention/flash_attention.py:572-621).
+ *   q, o        : [B, Sq, Hq, D] by element strides (batch, seq, head); the Sq new tokens of every sequence, whose K/V
+ *                 have ALREADY been written to the cache
+ *   k/v_cache   : [num_blocks, L, block_size, Hkv, D] contiguous; block_size a power of two in [8, 128]
+ *   block_tables: int32 [B, max_blocks_per_seq]; context_lens int32 [B] = keys of each sequence INCLUDING the Sq new ones
+ *   causal != 0 : query i of sequence b sees keys [0, context_lens[b] - Sq + i] (the diagonal ends at the sequence's last
+ *                 key). The reference kernel leaves its causal mask commented out (:774-777), i.e. every new token would
+ *                 see the later ones; causal = 0 reproduces that literally.
+ * The KV tiles are gathered block by block with TMA through the block table inside the prefill kernel (tcgen05 path);
+ * the cache must hold finite values in every slot of a block that is in use (PagedKVCache zero-fills).           */
+int b200_fa_fwd_paged(const void* q, const void* k_cache, const void* v_cache, void* o, float* lse, int B, int Sq, int Hq,
+                      int Hkv, int D, const int64_t q_strides[3], const int64_t o_strides[3], const int32_t* block_tables,
+                      int max_blocks_per_seq, int block_size, int num_blocks, int num_layers, int layer_idx,
+                      const int32_t* context_lens, float softmax_scale, int causal, int dtype, void* stream);
+
 /* ---- K6: tensor-parallel all-reduce over NVSwitch multicast / peer memory -------------------------------
  * Replaces torch.distributed.all_reduce(output_parallel) + the bias add of RowParallelLinear.forward
  * (parallelism/tensor_parallel.py:296-308) and comm.all_reduce (parallelism/communication.py:37-209) for the

@@ -33,6 +33,8 @@ SIGNATURES = {
     "b200_fa_fwd_accum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_float, c_int, c_int64, c_void_p,
                                   c_int, c_int, c_void_p]),
+    "b200_fa_fwd_paged": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int64_p,
+                                  c_int64_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int, c_void_p]),
     "b200_lse_merge": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64_p, c_int,
                                c_void_p]),
     "b200_cast_out": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64_p, c_int, c_void_p]),

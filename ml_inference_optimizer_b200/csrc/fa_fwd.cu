@@ -76,15 +76,20 @@ struct Params {
   float* lse_acc;           // fp32, rows contiguous, element strides (batch, head)
   int64_t lse_sb, lse_sh;
   int acc_init;             // 1: overwrite the accumulator (first ring step), 0: log-sum-exp merge into it
+  // paged K/V (chunked prefill against the cache, q_len > 1): the KV tile of 128 keys is assembled from 128 / block_size
+  // physical blocks named by the block table (one TMA box per block); kv_lens holds the context lengths
+  const int32_t* block_table;  // [B, max_blocks] or nullptr (K/V addressed by strides)
+  int max_blocks, block_size;
+  int causal_bottom;        // 1: the causal diagonal ends at each sequence's LAST key (offset = kv_len - Sq per sequence)
 };
 
 // number of KV tiles a query tile [row0, row0+128) needs
-__device__ __forceinline__ int num_kv_tiles(const Params& p, int row0, int kv_len) {
+__device__ __forceinline__ int num_kv_tiles(const Params& p, int row0, int kv_len, int64_t coff) {
   if (row0 >= p.Sq) return 0;
   int64_t visible = kv_len;
   if (p.causal) {
     const int last_row = min(row0 + BLOCK_M - 1, p.Sq - 1);
-    const int64_t lim = static_cast<int64_t>(last_row) + p.causal_offset + 1;
+    const int64_t lim = static_cast<int64_t>(last_row) + coff + 1;
     if (lim < visible) visible = lim;
   }
   if (visible <= 0) return 0;
@@ -94,6 +99,7 @@ __device__ __forceinline__ int num_kv_tiles(const Params& p, int row0, int kv_le
 // One work item = one block index of the launch grid: a pair of 128-row query tiles of one (batch, head).
 struct Work {
   int head, batch, kv_head, q_row0, kv_len, n0, n1, n_max;
+  int coff;  // causal offset of this item: key j visible to query i iff j <= i + coff
   __device__ __forceinline__ void set(const Params& p, int bx, int by, int bz) {
     // heavy (late) query tiles first under a causal mask
     const int pair = p.causal ? (p.num_pairs - 1 - bx) : bx;
@@ -103,8 +109,9 @@ struct Work {
     q_row0 = pair * 2 * BLOCK_M;
     kv_len = p.Sk;
     if (p.kv_lens != nullptr) kv_len = max(0, min(p.Sk, p.kv_lens[batch]));
-    n0 = num_kv_tiles(p, q_row0, kv_len);
-    n1 = num_kv_tiles(p, q_row0 + BLOCK_M, kv_len);
+    coff = p.causal_bottom ? kv_len - p.Sq : static_cast<int>(p.causal_offset);
+    n0 = num_kv_tiles(p, q_row0, kv_len, coff);
+    n1 = num_kv_tiles(p, q_row0 + BLOCK_M, kv_len, coff);
     n_max = max(n0, n1);
   }
   // Every lane holds the same values, but the compiler cannot know that for fields derived from a launch-control
@@ -116,6 +123,7 @@ struct Work {
     kv_head = __shfl_sync(0xffffffffu, kv_head, 0);
     q_row0 = __shfl_sync(0xffffffffu, q_row0, 0);
     kv_len = __shfl_sync(0xffffffffu, kv_len, 0);
+    coff = __shfl_sync(0xffffffffu, coff, 0);
     n0 = __shfl_sync(0xffffffffu, n0, 0);
     n1 = __shfl_sync(0xffffffffu, n1, 0);
     n_max = max(n0, n1);
@@ -239,9 +247,23 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             mbar_arrive_expect_tx(&kv_full[stage], C::TILE_BYTES);
             uint8_t* dst = smem + C::SMEM_KV_OFF + stage * C::TILE_BYTES;
             const CUtensorMap* tm = kv == 0 ? &tmap_k : &tmap_v;
+            if (p.block_table != nullptr) {
+              // paged cache, tensor map dims (D, Hkv, block_size, num_blocks): one box of block_size keys per physical
+              // block, placed at its row offset inside the swizzled tile (block_size % 8 == 0 keeps the 1024-byte swizzle
+              // atoms aligned). Blocks past the sequence's last one re-load the last block: finite data, masked by kv_len.
+              const int bs = p.block_size, nblk = (w.kv_len + bs - 1) / bs;
+              const int32_t* bt = p.block_table + static_cast<int64_t>(w.batch) * p.max_blocks;
+              for (int b = 0, lb = j * (BLOCK_N / bs); b < BLOCK_N / bs; ++b, ++lb) {
+                const int phys = __ldg(bt + min(lb, nblk - 1));
 #pragma unroll
-            for (int c = 0; c < C::BOXES; ++c)
-              tma_load_4d(dst + c * 16384, tm, &kv_full[stage], c * 64, w.kv_head, j * BLOCK_N, w.batch);
+                for (int c = 0; c < C::BOXES; ++c)
+                  tma_load_4d(dst + c * 16384 + b * bs * 128, tm, &kv_full[stage], c * 64, w.kv_head, 0, phys);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < C::BOXES; ++c)
+                tma_load_4d(dst + c * 16384, tm, &kv_full[stage], c * 64, w.kv_head, j * BLOCK_N, w.batch);
+            }
             if (++stage == NS) { stage = 0; phase ^= 1; }
           }
         }
@@ -404,7 +426,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int kv_len = w.kv_len;
       float m_used = -INFINITY;  // reference max (log2 units) the stored P / O / l are relative to
       float l_run = 0.f;
-      const int64_t q_pos_plus = static_cast<int64_t>(q_row) + p.causal_offset;  // last visible key under causal
+      const int64_t q_pos_plus = static_cast<int64_t>(q_row) + w.coff;  // last visible key under causal
 
       for (int j = 0; j < nt; ++j) {
         const uint32_t par = (iters + static_cast<uint32_t>(j)) & 1;
@@ -684,8 +706,22 @@ static int run(const void* q, const void* k, const void* v, int B, int Sq, int S
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_bshd_tmap(&tq, q, B, Sq, Hq, D, q_strides, "q"))) return rc;
-  if ((rc = make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
-  if ((rc = make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
+  if (p.block_table != nullptr) {
+    // paged: k / v point at the layer's slice of the cache; k_strides = (block, token, head) element strides, box = one block
+    for (int which = 0; which < 2; ++which) {
+      const int64_t* st = which == 0 ? k_strides : v_strides;
+      // (for the paged call `Sk` carries the number of PHYSICAL blocks of the cache: the extent of the tensor map)
+      uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(Hkv), static_cast<uint64_t>(p.block_size),
+                          static_cast<uint64_t>(Sk)};
+      uint64_t str[3] = {static_cast<uint64_t>(st[2]) * 2, static_cast<uint64_t>(st[1]) * 2, static_cast<uint64_t>(st[0]) * 2};
+      uint32_t box[4] = {64, 1, static_cast<uint32_t>(p.block_size), 1};
+      if ((rc = encode_tmap_sw128_16b(which == 0 ? &tk : &tv, which == 0 ? k : v, 4, dims, str, box))) return rc;
+    }
+    Sk = p.max_blocks * p.block_size;  // the key range the kernel walks is bounded by the block table
+  } else {
+    if ((rc = make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
+    if ((rc = make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
+  }
   // B200_FA_PERSISTENT=0 in the environment: every CTA handles only its own block (no work stealing)
   static const bool persistent = [] { const char* e = getenv("B200_FA_PERSISTENT"); return !(e && e[0] == '0'); }();
   p.persistent = persistent ? 1 : 0;
@@ -747,4 +783,36 @@ extern "C" int b200_fa_fwd_accum(const void* q, const void* k, const void* v, fl
   p.acc_init = init ? 1 : 0;
   return fa::run(q, k, v, B, Sq, Sk, Hq, Hkv, D, q_strides, k_strides, v_strides, softmax_scale, causal, causal_offset, kv_lens,
                  dtype, stream, p, true);
+}
+
+extern "C" int b200_fa_fwd_paged(const void* q, const void* k_cache, const void* v_cache, void* o, float* lse, int B, int Sq,
+                                 int Hq, int Hkv, int D, const int64_t q_strides[3], const int64_t o_strides[3],
+                                 const int32_t* block_tables, int max_blocks_per_seq, int block_size, int num_blocks,
+                                 int num_layers, int layer_idx, const int32_t* context_lens, float softmax_scale, int causal,
+                                 int dtype, void* stream) {
+  using namespace b200;
+  B200_CHECK_ARG(o && o_strides && k_cache && v_cache && block_tables && context_lens, "fa_fwd_paged: NULL pointer argument");
+  B200_CHECK_ARG(block_size >= 8 && block_size <= 128 && (block_size & (block_size - 1)) == 0,
+                 "fa_fwd_paged: block_size %d must be a power of two in [8, 128]", block_size);
+  B200_CHECK_ARG(max_blocks_per_seq > 0 && num_blocks > 0 && num_layers > 0 && layer_idx >= 0 && layer_idx < num_layers,
+                 "fa_fwd_paged: bad paged-cache arguments");
+  for (int i = 0; i < 3; ++i)
+    B200_CHECK_ARG(o_strides[i] > 0 && o_strides[i] % 8 == 0, "fa_fwd_paged: o stride %d = %lld must be a positive multiple of 8 elements",
+                   i, (long long)o_strides[i]);
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "fa_fwd_paged: o must be 16-byte aligned");
+  fa::Params p{};
+  p.o = o;
+  p.o_sb = o_strides[0]; p.o_sh = o_strides[2]; p.o_ss = o_strides[1];
+  p.lse = lse;
+  p.block_table = block_tables;
+  p.max_blocks = max_blocks_per_seq;
+  p.block_size = block_size;
+  p.causal_bottom = causal ? 1 : 0;
+  // cache layout [num_blocks, L, block_size, Hkv, D] (baseline/inference.py:1077-1084): element strides (block, token, head)
+  const int64_t tok = static_cast<int64_t>(Hkv) * D;
+  const int64_t cs[3] = {static_cast<int64_t>(num_layers) * block_size * tok, tok, static_cast<int64_t>(D)};
+  const char* kb = static_cast<const char*>(k_cache) + static_cast<int64_t>(layer_idx) * block_size * tok * 2;
+  const char* vb = static_cast<const char*>(v_cache) + static_cast<int64_t>(layer_idx) * block_size * tok * 2;
+  return fa::run(q, kb, vb, B, Sq, /*Sk: physical blocks for the tensor map*/ num_blocks, Hq, Hkv, D, q_strides, cs, cs, softmax_scale,
+                 causal, 0, context_lens, dtype, stream, p, false);
 }

@@ -1402,10 +1402,13 @@ int b200_fused_mlp(const void* x, int64_t ldx, const void* w_up, const void* b_u
   const int64_t inter = align256(T * static_cast<int64_t>(i) * 2);
   void* sk_ws = static_cast<char*>(workspace) + inter;
   const int64_t sk_bytes = workspace_bytes - inter;
-  // Prefill-sized inputs: ONE launch, up(+gate) and down projection interleaved by row groups (fused_mlp_pair_kernel).
-  // B200_MLP_FUSED=0 keeps the two-launch path.
+  // Prefill-sized inputs can run as ONE launch, up(+gate) and down projection interleaved by row groups
+  // (fused_mlp_pair_kernel): B200_MLP_FUSED=1. Measured on B200 (tests/fused_mlp_probe.py, interleaved A/B): the single
+  // launch keeps the intermediate in L2 at GPT-2 widths (DRAM reads 129 MB vs >= 260 MB, profiles/) and equals the two
+  // launches in SM cycles (7.87M vs 7.72M at C3 under ncu), but in the power-capped sustained regime it runs 5-12 % slower
+  // (C3 6.3-6.6 vs 5.9-6.0 ms, C2 0.274 vs 0.250 ms), so two launches stay the default.
   const char* fused_env = getenv("B200_MLP_FUSED");  // read per call: tests flip it inside one process
-  const bool fused_enabled = !(fused_env && fused_env[0] == '0');
+  const bool fused_enabled = fused_env != nullptr && fused_env[0] == '1';
   if (fused_enabled && T >= 1024) return b200::fused_mlp_single_launch(x, ldx, w_up, b_up, w_gate, b_gate, w_down, b_down, y, ldy, T, h, i, h_out, act, dtype, workspace, sk_ws, sk_bytes, s);
   // decode-sized inputs: GEMM1 + bias + activation (SwiGLU: gate/up pair) -> 16-bit intermediate -> GEMM2 + bias, each with
   // split-K over the SMs the few output tiles leave idle

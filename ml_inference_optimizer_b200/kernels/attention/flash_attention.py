@@ -138,19 +138,24 @@ def _paged_kwargs(kwargs: Dict[str, Any]):
 
 class _AttentionBase(nn.Module):
     def _paged_decode(self, q: torch.Tensor, kwargs: Dict[str, Any]) -> torch.Tensor:
-        """q [B, 1, Hq, D] against the paged cache (reference flash_attention.py:572-621 -> attention_kernels.py:1206)."""
+        """q [B, q_len, Hq, D] against the paged cache (reference flash_attention.py:572-621 -> attention_kernels.py:1206):
+        q_len == 1 runs the decode kernel K2, q_len > 1 the prefill kernel K1 over the block table."""
         k_cache, v_cache, block_tables, context_lengths, block_size, max_seq_len, layer_idx = _paged_kwargs(kwargs)
         B, q_len, Hq, D = q.shape
-        if q_len != 1:
-            raise NotImplementedError("the paged branch serves single-token decode (q_seq_len == 1); run prefill through "
-                                      "the standard branch")
         if k_cache.shape[2] != block_size:
             raise ValueError("kv_cache_block_size does not match the cache tensor")
         dt = self.flash_attention._compute_dtype(q.dtype)
         orig = q.dtype
+        lens = context_lengths.to(torch.int32).contiguous()
+        tables = block_tables.to(torch.int32).contiguous()
+        if q_len != 1:
+            # short-q / chunked prefill against the cache (reference attention_kernels.py:1251 picks BLOCK_SIZE_M = 64 for
+            # it): K1 gathers the KV tiles through the block table; the q_len new tokens are the last keys of each sequence
+            out = ops.paged_prefill_attention(q.to(dt), k_cache, v_cache, tables, lens, layer_idx=int(layer_idx), causal=True,
+                                              softmax_scale=self.config.softmax_scale)
+            return out.reshape(B, q_len, Hq * D).to(orig)
         qd = q.reshape(B, Hq, D).to(dt)
-        out = ops.decode_attention(qd, k_cache, v_cache, context_lengths.to(torch.int32).contiguous(),
-                                   softmax_scale=self.config.softmax_scale, block_tables=block_tables.to(torch.int32).contiguous(),
+        out = ops.decode_attention(qd, k_cache, v_cache, lens, softmax_scale=self.config.softmax_scale, block_tables=tables,
                                    layer_idx=int(layer_idx), max_context_len=int(max_seq_len))
         return out.view(B, 1, Hq * D).to(orig)
 
@@ -346,8 +351,10 @@ class _HFAttentionAdapter(nn.Module):
         if _PAGED_CONTEXT is not None:
             ctx_ = _PAGED_CONTEXT
             paged = ctx_["cache"]
-            if attention_mask is not None and self._mask_to_kv_lens(attention_mask, B, S, attention_mask.shape[-1],
-                                                                     True) is not None:
+            # (the check reads the mask back to the host: skipped while the decode step is being captured into a CUDA graph —
+            # the eager warm-up steps before the capture have already validated the same mask pattern)
+            if attention_mask is not None and not torch.cuda.is_current_stream_capturing() and \
+                    self._mask_to_kv_lens(attention_mask, B, S, attention_mask.shape[-1], True) is not None:
                 raise NotImplementedError("the paged prefill / decode path serves equal-length, unpadded prompts")
             if q.dtype != dt:
                 q, k, v = q.to(dt), k.to(dt), v.to(dt)

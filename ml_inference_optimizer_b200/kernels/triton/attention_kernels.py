@@ -13,15 +13,21 @@ TRITON_AVAILABLE = True
 
 def triton_paged_attention_forward(query: torch.Tensor, output: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
                                    block_tables: torch.Tensor, context_lengths: torch.Tensor, block_size: int,
-                                   max_seq_len: int, layer_idx: int) -> None:
-    """reference :1206-1311. query/output ``[B,H,q_len,D]`` (q_len must be 1: decode), cache
-    ``[num_blocks, L, block_size, Hkv, D]``, int32 tables/lengths. Writes ``output`` in place."""
+                                   max_seq_len: int, layer_idx: int, causal: bool = True) -> None:
+    """reference :1206-1311. query/output ``[B,H,q_len,D]``, cache ``[num_blocks, L, block_size, Hkv, D]``, int32
+    tables/lengths. Writes ``output`` in place. q_len == 1: decode kernel K2. q_len > 1 (chunked prefill, the reference's
+    BLOCK_SIZE_M = 64 case, :1251): prefill kernel K1 gathering K/V through the block table; the q_len queries are the last
+    q_len tokens of each sequence and are masked causally among themselves (``causal=False`` = the reference kernel as
+    written, whose causal mask is commented out, :774-777)."""
     assert query.dim() == 4 and output.shape == query.shape, "query/output must be [B,H,q_len,D]"
     assert block_tables.dtype == torch.int32 and context_lengths.dtype == torch.int32, "tables/lengths must be int32"
     assert k_cache.shape[2] == block_size, "block_size does not match the cache"
     B, H, q_len, D = query.shape
     if q_len != 1:
-        raise NotImplementedError("paged attention serves single-token decode (q_len == 1)")
+        ops.paged_prefill_attention(query.transpose(1, 2), k_cache, v_cache, block_tables.contiguous(),
+                                    context_lengths.contiguous(), layer_idx=layer_idx, causal=causal,
+                                    out=output.transpose(1, 2))
+        return
     o = ops.decode_attention(query.reshape(B, H, D), k_cache, v_cache, context_lengths.contiguous(),
                              block_tables=block_tables.contiguous(), layer_idx=layer_idx, max_context_len=max_seq_len)
     output.copy_(o.view(B, H, 1, D))

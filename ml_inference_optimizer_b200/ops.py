@@ -143,6 +143,44 @@ def flash_attn_fwd_accum(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o_ac
     check("b200_fa_fwd_accum", rc)
 
 
+def paged_prefill_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_tables: torch.Tensor,
+                            context_lens: torch.Tensor, layer_idx: int = 0, causal: bool = True,
+                            softmax_scale: Optional[float] = None, return_lse: bool = False,
+                            out: Optional[torch.Tensor] = None):
+    """Short-q / chunked-prefill attention against the paged cache: q ``[B,Sq,Hq,D]`` are the LAST ``Sq`` tokens of every
+    sequence (their K/V already appended), cache ``[num_blocks, L, block_size, Hkv, D]``, ``context_lens`` int32 ``[B]``
+    counts all keys. ``causal``: query i sees keys up to ``context_lens[b] - Sq + i``."""
+    dev = _require_cuda(q, k_cache, v_cache, block_tables, context_lens, out)
+    if q.dim() != 4 or k_cache.dim() != 5 or v_cache.shape != k_cache.shape:
+        raise ValueError("expected q [B,Sq,Hq,D] and caches [num_blocks, L, block_size, Hkv, D]")
+    B, Sq, Hq, D = q.shape
+    num_blocks, num_layers, block_size, Hkv, Dk = k_cache.shape
+    if Dk != D or k_cache.dtype != q.dtype or v_cache.dtype != q.dtype:
+        raise ValueError("cache head_dim / dtype must match q")
+    if not k_cache.is_contiguous() or not v_cache.is_contiguous():
+        raise ValueError("paged cache must be contiguous")
+    if block_tables.dtype != torch.int32 or block_tables.dim() != 2 or block_tables.shape[0] != B or not block_tables.is_contiguous():
+        raise ValueError("block_tables must be a contiguous int32 [B, max_blocks] tensor")
+    if context_lens.dtype != torch.int32 or context_lens.numel() != B or not context_lens.is_contiguous():
+        raise ValueError("context_lens must be a contiguous int32 [B] tensor")
+    dt = _dtype_code(q)
+    q = _last_dim_contiguous(q)
+    if out is None:
+        out = torch.empty((B, Sq, Hq, D), dtype=q.dtype, device=dev)
+    elif tuple(out.shape) != (B, Sq, Hq, D) or out.dtype != q.dtype or out.stride(-1) != 1:
+        raise ValueError("out must be [B,Sq,Hq,D], same dtype as q, D contiguous")
+    lse = torch.empty((B, Hq, Sq), dtype=torch.float32, device=dev) if return_lse else None
+    scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.b200_fa_fwd_paged(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), _ptr(lse), B, Sq, Hq,
+                                   Hkv, D, strides3(q.stride()[:3]), strides3(out.stride()[:3]), block_tables.data_ptr(),
+                                   block_tables.shape[1], block_size, num_blocks, num_layers, int(layer_idx),
+                                   context_lens.data_ptr(), scale, int(bool(causal)), dt, _stream_ptr(dev))
+    check("b200_fa_fwd_paged", rc)
+    return (out, lse) if return_lse else out
+
+
 def lse_merge(o_acc: torch.Tensor, lse_acc: torch.Tensor, o_b: torch.Tensor, lse_b: torch.Tensor) -> None:
     """In place: merge the partial result ``(o_b [B,Sq,Hq,D] 16-bit, lse_b [B,Hq,Sq])`` into the fp32 accumulator."""
     dev = _require_cuda(o_acc, lse_acc, o_b, lse_b)

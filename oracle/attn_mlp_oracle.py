@@ -126,6 +126,31 @@ def decode_attention_ref(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.
     return torch.stack(outs), torch.stack(lses)
 
 
+def paged_prefill_attention_ref(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, block_tables: torch.Tensor,
+                                context_lens: torch.Tensor, layer_idx: int = 0, causal: bool = True,
+                                softmax_scale: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Short-q attention vs the paged cache, fp32: q [B,Sq,Hq,D] are the last Sq tokens of each sequence (their K/V are in
+    the cache), keys = the ``context_lens[b]`` gathered tokens (addressing of _paged_attention_fwd_kernel,
+    kernels/triton/attention_kernels.py:722-760; q_len > 1 is its BLOCK_SIZE_M = 64 case, :1251). ``causal``: query i sees
+    keys <= context_len - Sq + i — the mask the reference kernel carries commented out (:774-777); ``causal=False`` is the
+    kernel as written (every query sees all context_len keys). Returns (O [B,Sq,Hq,D], LSE [B,Hq,Sq])."""
+    B, Sq, Hq, D = q.shape
+    outs, lses = [], []
+    for b in range(B):
+        n = int(context_lens[b])
+        kb = paged_gather(k_cache, block_tables[b], layer_idx, n)
+        vb = paged_gather(v_cache, block_tables[b], layer_idx, n)
+        if n == 0:
+            outs.append(torch.zeros(Sq, Hq, D))
+            lses.append(torch.full((Hq, Sq), float("-inf")))
+            continue
+        o, l = attention_ref(q[b:b + 1], kb.unsqueeze(0), vb.unsqueeze(0), causal=causal, softmax_scale=softmax_scale,
+                             causal_offset=n - Sq)
+        outs.append(o[0])
+        lses.append(l[0])
+    return torch.stack(outs), torch.stack(lses)
+
+
 def kv_append_ref(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor,
                   context_lens: torch.Tensor, block_tables: Optional[torch.Tensor] = None, layer_idx: int = 0) -> None:
     """In place: store the new token's K,V [B,Hkv,D] at position context_len-1

@@ -268,6 +268,41 @@ def test_decode_paged_and_kv_append(ops):
     check_lse(lse, rl)
 
 
+@pytest.mark.parametrize("Sq,Hq,Hkv,D,block_size,causal", [
+    (64, 8, 8, 128, 16, True),      # the reference's BLOCK_SIZE_M = 64 case
+    (200, 8, 2, 128, 16, True),     # GQA, q tile pair partly empty, ragged context lengths
+    (300, 4, 4, 64, 32, True),      # D = 64, two q tiles + a third partial
+    (48, 4, 1, 128, 8, False),      # MQA, smallest block; the reference kernel as written (no causal mask)
+    (128, 4, 4, 128, 128, True),    # one physical block per KV tile
+])
+def test_paged_short_q_attention_vs_oracle(ops, Sq, Hq, Hkv, D, block_size, causal):
+    """VERDICT r1 missing #4: q_len > 1 against the paged cache (chunked prefill) — K1 gathering K/V through the block
+    table, vs the oracle's gather + exact attention with the diagonal ending at each sequence's last key."""
+    B, L, layer = 3, 2, 1
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ctx = torch.tensor([Sq + 517, Sq, Sq + 130], dtype=torch.int32)       # includes a sequence with no history at all
+    max_blocks = (int(ctx.max()) + block_size - 1) // block_size + 1
+    num_blocks = B * max_blocks + 3
+    kc = torch.randn(num_blocks, L, block_size, Hkv, D, device="cuda", dtype=torch.bfloat16, generator=g)
+    vc = torch.randn(num_blocks, L, block_size, Hkv, D, device="cuda", dtype=torch.bfloat16, generator=g)
+    perm = torch.randperm(num_blocks, generator=torch.Generator().manual_seed(5))[:B * max_blocks]
+    bt = perm.view(B, max_blocks).to(torch.int32)                           # scattered, non-monotonic physical blocks
+    q = torch.randn(B, Sq, Hq, D, device="cuda", dtype=torch.bfloat16, generator=g)
+    o, lse = ops.paged_prefill_attention(q, kc, vc, bt.cuda(), ctx.cuda(), layer_idx=layer, causal=causal, return_lse=True)
+    ro, rl = orc.paged_prefill_attention_ref(q.cpu(), kc.cpu(), vc.cpu(), bt, ctx, layer_idx=layer, causal=causal)
+    check_out(o, ro)
+    check_lse(lse, rl)
+    # the functional shim of the reference signature ([B,H,q,D] in and out) goes the same way
+    from ml_inference_optimizer_b200.kernels.triton.attention_kernels import triton_paged_attention_forward
+    out = torch.empty(B, Hq, Sq, D, device="cuda", dtype=torch.bfloat16)
+    triton_paged_attention_forward(q.transpose(1, 2).contiguous(), out, kc, vc, bt.cuda(), ctx.cuda(), block_size, max_blocks * block_size,
+                                   layer, causal=causal)
+    assert torch.equal(out.transpose(1, 2), o)
+    if causal:  # the last query row is exactly a decode step over the same cache
+        od = ops.decode_attention(q[:, -1].contiguous(), kc, vc, ctx.cuda(), block_tables=bt.cuda(), layer_idx=layer)
+        assert (od.float() - o[:, -1].float()).abs().max().item() <= 2e-2
+
+
 def test_decode_equals_last_prefill_row(ops):
     B, S, Hq, Hkv, D = 2, 1024, 8, 2, 128
     q, k, v = rand_qkv(B, S, S, Hq, Hkv, D, seed=3)
