@@ -149,12 +149,18 @@ def bind_to_gpu_numa_node(dev_index):
     """Pin this process (and therefore the first-touch placement of its pinned host buffers) to the CPUs of the NUMA
     node the GPU hangs off. With 8 ranks allocating on node 0 the e2e leg of round 1 ran at 0.25 efficiency."""
     try:
-        import torch
-        p = torch.cuda.get_device_properties(dev_index)
-        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[dev_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else dev_index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()
+        if len(bdf.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bdf = bdf[4:]
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
         if node < 0:
-            return None
+            return {"numa_node": node, "note": "single NUMA domain: nothing to bind"}
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -164,9 +170,9 @@ def bind_to_gpu_numa_node(dev_index):
         if use:
             os.sched_setaffinity(0, use)
             return {"numa_node": node, "cpus": len(use)}
-    except Exception:  # noqa: BLE001
-        pass
-    return None
+        return {"numa_node": node, "note": "no allowed CPU on the GPU's node"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:120]}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -324,7 +330,7 @@ def parity_check(cx):
     T, h, i = 512, 512, 1024 * n
     rn = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).bfloat16()
     x, wu, bu, wg, bg, wd, bd = rn(T, h), rn(i, h, sc=0.03), rn(i, sc=0.1), rn(i, h, sc=0.03), rn(i, sc=0.1), rn(h, i, sc=0.03), rn(h, sc=0.1)
-    ref = orc.tp_mlp_ref(x, wu, bu, wd, bd, "swiglu", n, wg, bg)
+    ref, partial_abs = orc.tp_mlp_ref(x, wu, bu, wd, bd, "swiglu", n, wg, bg, return_partial_abs_sum=True)
     c = lambda t: t.to(dev)
     reduce_impl = "none"
     if n > 1:
@@ -344,12 +350,14 @@ def parity_check(cx):
         y = ops.fused_mlp(c(x), c(wu), c(bu), c(wd), c(bd), "swiglu", c(wg), c(bg))
         tp_err = (y.float().cpu() - ref).abs().max().item()
     tp_scale = ref.abs().max().item()
+    tp_tol = orc.tp_mlp_tolerance(ref, partial_abs, n, multicast="multicast" in reduce_impl)
     ring_o, ring_l, tp_err = cx.max_over_ranks([ring_o, ring_l, tp_err])
     out = {"ring_max_abs": ring_o, "ring_lse_max_abs": ring_l, "tp_max_abs": tp_err, "tp_ref_max_abs": tp_scale,
-           "bounds": {"ring_max_abs": 2e-2, "ring_lse_max_abs": 1e-2, "tp_max_abs": "2e-2 * max(1, |ref|max / 4)"},
+           "bounds": {"ring_max_abs": 2e-2, "ring_lse_max_abs": 1e-2, "tp_max_abs": tp_tol,
+                      "tp_rule": "2e-2*max(1,|ref|max/4) + 2^-9*max sum_r|partial_r| (bf16 partials) + 2^-8*|ref|max (switch rounding); oracle.tp_mlp_tolerance"},
            "shapes": f"ring: causal {part} B{B} S{S} Hq{Hq} Hkv{Hkv} D{D}; tp: SwiGLU T{T} {h}->{i}->{h}",
            "tp_reduce": reduce_impl, "checker": "oracle/attn_mlp_oracle.py (fp32, CPU)"}
-    ok = ring_o <= 2e-2 and ring_l <= 1e-2 and tp_err <= 2e-2 * max(1.0, tp_scale / 4)
+    ok = ring_o <= 2e-2 and ring_l <= 1e-2 and tp_err <= tp_tol
     if not ok:
         raise SystemExit(f"parity check failed before timing: {json.dumps(out)}")
     return out
@@ -581,10 +589,9 @@ def tp_breakdown_leg(cx, w, st, args):
         buf = pool["bufs"][0]
         t = buf.view((st["T"], w["h"]), torch.bfloat16)
         ar = cx.timed(lambda: buf.all_reduce_(t, down.bias, max_ctas=mlp.comm_ctas_single), 2, 5)
-        ar_few = cx.timed(lambda: buf.all_reduce_(t, down.bias, max_ctas=mlp.comm_ctas), 1, 3)
         buf.check()
-        out.update({"allreduce_alone_ms": ar, "allreduce_alone_ms_with_overlap_cta_count": ar_few,
-                    "allreduce_impl": "K6 " + ("multicast" if buf.multicast else "peer"), "allreduce_ctas": [mlp.comm_ctas_single, mlp.comm_ctas]})
+        out.update({"allreduce_alone_ms": ar, "allreduce_impl": "K6 " + ("multicast" if buf.multicast else "peer"),
+                    "allreduce_ctas": mlp.comm_ctas_single or "one per SM (co-resident with the GEMM CTAs)"})
     nccl = cx.timed(lambda: cx.dist.all_reduce(y), 2, 5)
     out["nccl_allreduce_alone_ms"] = nccl
     bus = 2.0 * (n - 1) / n * payload
@@ -753,7 +760,7 @@ def run_ours(args, w):
     breakdown = tp_breakdown_leg(cx, w, st, args) if n > 1 else None
     reduce_impl = st["mlp_module"].last_reduce if st["mlp_module"] is not None else None
     chunks = st["mlp_module"].overlap_chunks if st["mlp_module"] is not None else None
-    comm_ctas = st["mlp_module"].comm_ctas if st["mlp_module"] is not None else None
+    comm_ctas = (st["mlp_module"].comm_ctas or "one per SM, co-resident with the GEMM CTAs") if st["mlp_module"] is not None else None
     T = st["T"]
     del st, step
     torch.cuda.empty_cache()

@@ -222,7 +222,7 @@ int b200_fa_fwd_paged(const void* q, const void* k_cache, const void* v_cache, v
  * multimem.ld_reduce (fp32 accumulation inside the switch), optionally adds `bias` ([ncols], region = whole rows of
  * ncols elements) and broadcasts it with multimem.st. `flag_offset` names b200_tp_allreduce_flag_bytes() bytes inside
  * the symmetric buffer, zeroed once at creation; `epoch` must advance by 2 per call on that buffer, identically on all
- * ranks (the first call uses 1). All ranks must pass identical sizes and `max_ctas` (0 = 32; <= 64). Spins are bounded:
+ * ranks (the first call uses 1). All ranks must pass identical sizes and `max_ctas` (0 = one per SM; <= 160). Spins are bounded:
  * on a timeout (a peer never arrived) *error_flag (device int) is set to 1 and the kernel returns.            */
 int64_t b200_tp_allreduce_flag_bytes(void);
 int b200_tp_allreduce(void* multicast_base, void* const* peer_bases, int world, int rank, int64_t data_offset,

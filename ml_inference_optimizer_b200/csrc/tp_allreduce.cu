@@ -11,8 +11,8 @@
 //   accumulation of the bf16/fp16 partials, one 16-byte vector per instruction), the optional bias is added once, and
 //   multimem.st  broadcasts the reduced vector back to all ranks through the switch.
 // Per GPU that is payload/world bytes in, payload/world out on the reduce side and the same on the broadcast side — the
-// minimum NVLink traffic for an all-reduce — and it needs only a few CTAs (the reduction happens in the switch), so the
-// GEMMs of the next token chunk keep their SMs. Without multicast support the same kernel reads the peers' slices with
+// minimum NVLink traffic for an all-reduce — and the reduction happens in the switch, so the CTAs only issue loads and
+// stores: they are built to share SMs with the GEMMs of the next token chunk (see THREADS below). Without multicast support the same kernel reads the peers' slices with
 // plain loads over their unicast mappings, sums in fp32 and stores to every peer.
 //
 // Synchronisation: per-CTA flag slots inside the symmetric buffer (`flags[cta][src_rank]`, monotonically increasing
@@ -26,9 +26,14 @@ namespace b200 {
 namespace ar {
 
 constexpr int MAX_WORLD = 8;
-constexpr int MAX_CTAS = 64;
-constexpr int THREADS = 512;
-constexpr int UNROLL = 8;
+// Small CTAs with few registers and no shared memory: a CTA of this kernel fits on an SM NEXT TO a resident CTA of the
+// persistent GEMM (209 regs x 256 threads + 227 KB smem leave ~12K registers and the 1 KB CTA reservation free), so the
+// all-reduce of token chunk c runs underneath the GEMMs of chunk c+1 without taking SMs away from them. Its warps mostly
+// wait on NVLink round trips; bytes in flight = CTAs x 256 threads x 4 x 16 B (2.4 MB at one CTA per SM).
+constexpr int MAX_CTAS = 160;
+constexpr int THREADS = 256;
+constexpr int UNROLL = 4;
+constexpr int MIN_CTAS_PER_SM = 6;  // caps the kernel at 42 registers per thread
 constexpr long long SPIN_TIMEOUT_CYCLES = 6000000000LL;  // ~3 s at 2 GHz
 
 struct Params {
@@ -116,7 +121,7 @@ __device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
 }
 
 template <typename T, bool MULTICAST>
-__global__ void __launch_bounds__(THREADS, 1) tp_allreduce_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, MIN_CTAS_PER_SM) tp_allreduce_kernel(const Params p) {
   cross_rank_barrier(p, p.epoch);  // every rank's partial rows are complete and visible
 
   const long long total_vec = p.nbytes >> 4;
@@ -199,7 +204,7 @@ int b200_tp_allreduce(void* multicast_base, void* const* peer_bases, int world, 
   p.bias = bias;
   p.ncols = bias != nullptr ? ncols : 8;
   p.error_flag = error_flag;
-  int ctas = max_ctas > 0 ? max_ctas : 32;
+  int ctas = max_ctas > 0 ? max_ctas : sm_count();
   if (ctas > ar::MAX_CTAS) ctas = ar::MAX_CTAS;
   const long long per_rank_vec = ((nbytes >> 4) + world - 1) / world;
   const long long need = (per_rank_vec + ar::THREADS * ar::UNROLL - 1) / (ar::THREADS * ar::UNROLL);

@@ -169,8 +169,12 @@ class TensorParallelMLP(nn.Module):
         self.comm_sms = 32  # SMs left free for the collective while chunks are in flight (measured at tp=8: 2.02 -> 1.90 ms)
         # "auto": K6 over symmetric memory when it can be set up, else NCCL; "symmetric": K6 or raise; "nccl": NCCL only
         self.reduce_impl = os.environ.get("B200_TP_REDUCE", "auto")
-        self.comm_ctas = int(os.environ.get("B200_TP_COMM_CTAS", "16"))          # CTAs of K6 next to running GEMMs
-        self.comm_ctas_single = int(os.environ.get("B200_TP_COMM_CTAS_SINGLE", "48"))  # ... when nothing else runs
+        # K6 CTAs are small enough (256 threads, <= 42 registers, no shared memory) to sit on an SM next to a resident GEMM
+        # CTA: by default the GEMMs keep every SM (gemm_sm_reserve = 0) and K6 runs underneath them, one CTA per SM
+        # (measured at tp=8, C3: 4 chunks x 64 CTAs 1.11 ms, x 148 CTAs 1.40 ms, NCCL 1.71 ms, GEMMs alone 0.78 ms)
+        self.comm_ctas = int(os.environ.get("B200_TP_COMM_CTAS", "64"))           # 0 = one per SM
+        self.comm_ctas_single = int(os.environ.get("B200_TP_COMM_CTAS_SINGLE", "0"))
+        self.gemm_sm_reserve = int(os.environ.get("B200_TP_GEMM_SM_RESERVE", "0"))  # SMs withheld from the GEMMs while K6 runs
         # "copy": return a fresh tensor (safe default). "view": return the rows inside the symmetric buffer — valid
         # until the second-next TensorParallelMLP call on this group (two buffers rotate); saves one pass over [T, h].
         self.symmetric_output = "copy"
@@ -256,8 +260,9 @@ class TensorParallelMLP(nn.Module):
         n = self.overlap_chunks if T >= self.overlap_min_tokens else 1
         rows = ((T + n - 1) // n + 255) // 256 * 256
         bias = down.bias
-        if n > 1:
-            ops.set_sm_limit(max(2, ops.sm_count(x2.device) - self.comm_ctas))
+        reserve = self.gemm_sm_reserve if n > 1 else 0
+        if reserve > 0:
+            ops.set_sm_limit(max(2, ops.sm_count(x2.device) - reserve))
         try:
             for r0 in range(0, T, rows):
                 r1 = min(T, r0 + rows)
@@ -269,7 +274,7 @@ class TensorParallelMLP(nn.Module):
                 else:
                     buf.all_reduce_(out[r0:r1], bias, max_ctas=self.comm_ctas_single)
         finally:
-            if n > 1:
+            if reserve > 0:
                 ops.set_sm_limit(0)
         if n > 1:
             main.wait_stream(side)

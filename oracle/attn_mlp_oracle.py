@@ -264,20 +264,42 @@ def layernorm_ref(x, weight, bias=None, eps: float = 1e-5, residual=None, residu
     return weight.float() * x + (bias.float() if bias is not None else 0.0)
 
 
-def tp_mlp_ref(x, w_up, b_up, w_down, b_down, activation, tp: int, w_gate=None, b_gate=None) -> torch.Tensor:
+def tp_mlp_ref(x, w_up, b_up, w_down, b_down, activation, tp: int, w_gate=None, b_gate=None, return_partial_abs_sum: bool = False):
     """Column/row tensor-parallel MLP emulated serially: rank r holds rows [r*i/tp, (r+1)*i/tp) of W_up / W_gate
     and the matching columns of W_down (parallelism/tensor_parallel.py:130-135, :249-254); partial outputs are
-    summed (the all-reduce, :302) and the down bias is added once after the reduction (:304-308)."""
+    summed (the all-reduce, :302) and the down bias is added once after the reduction (:304-308).
+
+    ``return_partial_abs_sum``: also return max over elements of sum_r |partial_r| — the quantity that bounds what
+    rounding every rank's partial output to 16 bits before the all-reduce (as the reference does: the partials are in the
+    activation dtype) can cost: at most 2^-9 of it for bf16."""
     i = w_up.shape[0]
     assert i % tp == 0
     s = i // tp
-    total = None
+    total, abs_sum = None, None
     for r in range(tp):
         sl = slice(r * s, (r + 1) * s)
         h = linear_act_ref(x, w_up[sl], None if b_up is None else b_up[sl], activation,
                            None if w_gate is None else w_gate[sl], None if b_gate is None else b_gate[sl])
         part = torch.nn.functional.linear(h, w_down[:, sl].float())
         total = part if total is None else total + part
+        abs_sum = part.abs() if abs_sum is None else abs_sum + part.abs()
     if b_down is not None:
         total = total + b_down.float()
+    if return_partial_abs_sum:
+        return total, abs_sum.max().item()
     return total
+
+
+def tp_mlp_tolerance(ref: torch.Tensor, partial_abs_sum: float, tp: int, multicast: bool = True) -> float:
+    """Max-abs bound for the tensor-parallel MLP in bf16, term by term (no factor fitted to the rank count):
+      2e-2 * max(1, |ref|max / 4)   the single-GPU bound (GEMM arithmetic + one bf16 rounding of the result)
+      2^-9 * max sum_r |partial_r|  every rank rounds its partial output to bf16 before the reduction (tp > 1)
+      2^-8 * |ref|max               the NVSwitch's fp32 -> bf16 conversion of the reduced value is not round-to-nearest:
+                                    up to one ulp instead of half (measured, tests/symm_probe.py)"""
+    m = ref.abs().max().item()
+    tol = 2e-2 * max(1.0, m / 4)
+    if tp > 1:
+        tol += 2.0 ** -9 * partial_abs_sum
+        if multicast:
+            tol += 2.0 ** -8 * m
+    return tol

@@ -1,0 +1,13 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+N=${N:-8}
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/symm_probe.py > gpurun_out/r2_symm_probe_n$N.log 2>&1; echo rc=$?
+grep "probe\|FAIL" gpurun_out/r2_symm_probe_n$N.log | grep -v '"peer", "ctas": \(16\|32\)'
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 tests/tp_tune.py > gpurun_out/r2_tp_tune_n$N.log 2>&1; echo rc=$?
+grep "shape" gpurun_out/r2_tp_tune_n$N.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29544 tests/multi_gpu_check.py > gpurun_out/r2_mgc_n$N.log 2>&1; echo rc=$?
+grep "rank 0\|FAIL" gpurun_out/r2_mgc_n$N.log
+timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo rc=$?
+tail -c 2000 gpurun_out/r2_bench_n$N.err
+tail -c 7000 gpurun_out/r2_bench_n$N.json

@@ -52,7 +52,7 @@ def main():
             print(f"[rank {rank}] {mode} rows={rows} bias={with_bias}: max|err|={err:.3e} (tol {tol:.3e}) {'OK' if good else 'FAIL'}", flush=True)
         # bandwidth
         t = buf.view((T, h), torch.bfloat16)
-        for ctas in (8, 16, 32, 64):
+        for ctas in (16, 32, 64, 148):
             for _ in range(2):
                 buf.all_reduce_(t, max_ctas=ctas)
             torch.cuda.synchronize(); dist.barrier()
