@@ -152,7 +152,10 @@ int b200_fa_decode(const void* q, const void* k_cache, const void* v_cache, void
 
 /* ---- KV append: write the new token's K,V into the cache at position context_len-1 --------------------
  * Replaces triton_reshape_and_cache / _reshape_and_cache_kernel (attention_kernels.py:1314-1407, :811-905).
- *   key, value: [B, Hkv, D] contiguous (the reference's [B,1,Hkv,D]).                                    */
+ *   key, value: [B, Hkv, D] contiguous (the reference's [B,1,Hkv,D]).
+ *   Bounds: a position >= the cache capacity is DROPPED (never written into another sequence's rows): capacity =
+ *   max_blocks_per_seq * block_size for the paged layout; for the contiguous layout pass S_max as max_blocks_per_seq
+ *   (block_size = 0), 0 = unchecked. b200_fa_decode clamps context_lens to min(max_context_len, capacity) likewise.  */
 int b200_kv_append(const void* key, const void* value, void* k_cache, void* v_cache, int B, int Hkv, int D,
                    const int32_t* context_lens, int layout, int64_t kv_batch_stride, int64_t kv_token_stride,
                    const int32_t* block_table, int max_blocks_per_seq, int block_size, int num_layers,

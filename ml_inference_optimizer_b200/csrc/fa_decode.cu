@@ -47,6 +47,9 @@ struct Params {
   float scale_log2;     // softmax_scale * log2(e)
   int64_t kv_batch_stride, kv_token_stride;  // contiguous layout, elements
   int max_blocks_per_seq, block_size, num_layers, layer_idx;
+  int capacity;         // keys the cache of one sequence can hold: device-side context lengths are clamped to it, so a
+                        // length that ran past the cache (e.g. advanced on the device under a CUDA graph) cannot turn into
+                        // an out-of-bounds block-table read
 };
 
 template <int D, int G, typename T, bool PAGED>
@@ -66,7 +69,7 @@ decode_kernel(const Params p) {
   const int sub = lane % LPR;         // which 8-element slice of the row
   const int rsel = lane / LPR;        // which row of the warp-wide load
 
-  const int ctx = p.context_lens[b];
+  const int ctx = max(0, min(p.context_lens[b], p.capacity));
   // per-batch split range, aligned to TILE
   int chunk = (ctx + p.splits - 1) / p.splits;
   chunk = ((chunk + TILE - 1) / TILE) * TILE;
@@ -289,7 +292,7 @@ decode_gqa_mma_kernel(const Params p, const int G) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  const int ctx = p.context_lens[b];
+  const int ctx = max(0, min(p.context_lens[b], p.capacity));
   int chunk = (ctx + p.splits - 1) / p.splits;
   chunk = ((chunk + TILE - 1) / TILE) * TILE;
   const int k_begin = min(split * chunk, ctx);
@@ -481,10 +484,12 @@ __global__ void kv_append_kernel(const T* __restrict__ key, const T* __restrict_
                                  T* __restrict__ v_cache, const int32_t* __restrict__ context_lens, int row_elems,
                                  int layout, int64_t kv_batch_stride, int64_t kv_token_stride,
                                  const int32_t* __restrict__ block_table, int max_blocks_per_seq, int block_size,
-                                 int num_layers, int layer_idx) {
+                                 int num_layers, int layer_idx, int capacity) {
   const int b = blockIdx.x;
   const int pos = context_lens[b] - 1;  // the appended token is the last valid one (attention_kernels.py:862-866)
-  if (pos < 0) return;
+  // a position past the cache is dropped, never written: it would index beyond the block table / the sequence's rows and
+  // land in another sequence's block
+  if (pos < 0 || pos >= capacity) return;
   int64_t base;
   if (layout == B200_KV_PAGED) {
     const int bi = pos / block_size;
@@ -685,6 +690,9 @@ int b200_fa_decode(const void* q, const void* k_cache, const void* v_cache, void
   p.kv_batch_stride = kv_batch_stride; p.kv_token_stride = kv_token_stride;
   p.max_blocks_per_seq = max_blocks_per_seq; p.block_size = block_size; p.num_layers = num_layers;
   p.layer_idx = layer_idx;
+  // paged: what the block table can address; contiguous: the caller's bound on the lengths (ops.py passes S_max)
+  p.capacity = layout == B200_KV_PAGED ? (max_context_len < max_blocks_per_seq * block_size ? max_context_len : max_blocks_per_seq * block_size)
+                                       : max_context_len;
   const int G = Hq / Hkv;
   const bool paged = layout == B200_KV_PAGED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -709,11 +717,15 @@ int b200_kv_append(const void* key, const void* value, void* k_cache, void* v_ca
                        layer_idx >= 0 && layer_idx < num_layers,
                    "kv_append: bad paged-cache arguments");
   (void)dtype;  // a 16-bit copy: the element type does not matter
+  // capacity in tokens: paged = what the block table addresses; contiguous = max_blocks_per_seq when the caller passes the
+  // cache's S_max there (block_size == 0 marks that use), else unchecked
+  const int capacity = layout == B200_KV_PAGED ? max_blocks_per_seq * block_size
+                                               : (max_blocks_per_seq > 0 ? max_blocks_per_seq : 0x7fffffff);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   decode::kv_append_kernel<uint16_t><<<B, 128, 0, s>>>(
       static_cast<const uint16_t*>(key), static_cast<const uint16_t*>(value), static_cast<uint16_t*>(k_cache),
       static_cast<uint16_t*>(v_cache), context_lens, Hkv * D, layout, kv_batch_stride, kv_token_stride, block_table,
-      max_blocks_per_seq, block_size, num_layers, layer_idx);
+      max_blocks_per_seq, block_size, num_layers, layer_idx, capacity);
   B200_CUDA_OK(cudaGetLastError());
   note_launch("kv_append_kernel");
   return B200_OK;

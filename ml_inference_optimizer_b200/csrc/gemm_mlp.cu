@@ -54,6 +54,10 @@ struct Params {
   // L2 rasterisation: tiles are visited in groups of `group_m` row-blocks x all column-blocks, row-block fastest, so the
   // group's activation panel (group_m x BM rows) stays L2-resident while the weight is streamed once per group
   int group_m;
+  // L2 eviction hints of the TMA traffic (pair kernel): the activation panel of the raster group is re-read by the next
+  // waves (evict-last), a weight slab is shared by the CTAs of ONE wave and then dead until the next group (evict-first
+  // / normal), the output is written once
+  uint64_t hint_a, hint_b, hint_c;
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int tile_in, int& m_blk, int& n_blk, int& kb0, int& kb1) {
@@ -518,8 +522,8 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (P_A_STAGE_BYTES + P_B_STAGE_BYTES));
-          tma_load_2d_2sm(smem + P_SMEM_A_OFF + stage * P_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d_2sm(smem + P_SMEM_B_OFF + stage * P_B_STAGE_BYTES, tb, &full_bar[stage], kb * BK, brow);
+          tma_load_2d_2sm_hint(smem + P_SMEM_A_OFF + stage * P_A_STAGE_BYTES, &tmap_a, &full_bar[stage], kb * BK, m0, p.hint_a);
+          tma_load_2d_2sm_hint(smem + P_SMEM_B_OFF + stage * P_B_STAGE_BYTES, tb, &full_bar[stage], kb * BK, brow, p.hint_b);
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -624,7 +628,7 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (ep_tid == 0) {
-          tma_store_2d(&tmap_c, cs, n0 + chunk * 64, m0);
+          tma_store_2d_hint(&tmap_c, cs, n0 + chunk * 64, m0, p.hint_c);
           tma_store_commit();
         }
         cbuf ^= 1;
@@ -1199,13 +1203,28 @@ static int check_ptr16(const void* p, const char* name) {
 // y[T,N] = act(x[T,K] w[N,K]^T + b)      or      y = silu(x wg^T + bg) * (x w^T + b)  when act == SWIGLU
 // number of K splits for a problem with `tiles` output tiles and `kblocks` 64-wide K blocks: only skinny problems
 // (fewer output tiles than SMs) are split, into enough pieces to fill the machine, keeping >= 4 k-blocks per split
-static int choose_k_splits(int tiles, int kblocks) {
+static int choose_k_splits(int tiles, int kblocks, int64_t T, int n_blocks, int K) {
   const int sms = sm_count();
   if (tiles >= sms || kblocks < 8) return 1;
-  int splits = sms / tiles;  // one wave: every CTA resident at once, the fp32 reduce pass stays small
-  if (splits > kblocks / 4) splits = kblocks / 4;
-  if (splits > 32) splits = 32;
-  return splits < 1 ? 1 : splits;
+  // Skinny problems are weight-streaming bound and an SM can only pull so much: what matters is how many SMs stream at once.
+  // Cost model per candidate: bytes moved (weights + the fp32 partials written and re-read by the reduce pass) divided by
+  // the fraction of SM-waves that are full. (86 SwiGLU tiles of a T=64 Llama up-projection: 1 split = 58 % of the SMs,
+  // 5 splits = 430 CTAs = 2.9 waves = 97 %, for 56 MB of partials next to 180 MB of weights.)
+  const double w_bytes = static_cast<double>(n_blocks) * gemm::BN * K * 2.0;
+  const double part_bytes = 2.0 * static_cast<double>(T) * n_blocks * gemm::BN * 4.0;
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= 32 && kblocks / s >= 4; ++s) {
+    const int ctas = tiles * s;
+    const int waves = (ctas + sms - 1) / sms;
+    const double eff = static_cast<double>(ctas) / (static_cast<double>(waves) * sms);
+    const double cost = (w_bytes + (s > 1 ? s * part_bytes : 0.0)) / eff;
+    if (cost < best_cost * 0.98) {  // prefer fewer splits unless the gain is real
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
 }
 
 int64_t linear_act_workspace_bytes(int64_t T, int K, int N, int act) {
@@ -1213,7 +1232,7 @@ int64_t linear_act_workspace_bytes(int64_t T, int K, int N, int act) {
   const int out_cols = (act == B200_ACT_SWIGLU) ? 128 : 256;
   const int64_t m_blocks = (T + gemm::BM - 1) / gemm::BM, n_blocks = (N + out_cols - 1) / out_cols;
   if (m_blocks * n_blocks > 0x7fffffff) return 0;
-  const int splits = choose_k_splits(static_cast<int>(m_blocks * n_blocks), (K + gemm::BK - 1) / gemm::BK);
+  const int splits = choose_k_splits(static_cast<int>(m_blocks * n_blocks), (K + gemm::BK - 1) / gemm::BK, T, static_cast<int>(n_blocks), K);
   if (splits <= 1) return 0;
   return static_cast<int64_t>(splits) * T * n_blocks * gemm::BN * static_cast<int64_t>(sizeof(float));
 }
@@ -1278,7 +1297,7 @@ int linear_act_impl(const void* x, int64_t ldx, const void* w, const void* b, co
   const int64_t ws_need = linear_act_workspace_bytes(T, K, N, act);
   if (ws_need > 0 && workspace != nullptr && workspace_bytes >= ws_need &&
       (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
-    p.k_splits = choose_k_splits(p.num_m_blocks * p.num_n_blocks, p.num_k_blocks);
+    p.k_splits = choose_k_splits(p.num_m_blocks * p.num_n_blocks, p.num_k_blocks, T, p.num_n_blocks, K);
     p.partial = static_cast<float*>(workspace);
   }
   // large problems: CTA-pair kernel (256-row tiles). B200_GEMM_PAIR=0 in the environment keeps the single-CTA kernel.
@@ -1286,6 +1305,19 @@ int linear_act_impl(const void* x, int64_t ldx, const void* w, const void* b, co
   p.use_pair = (pair_enabled && p.k_splits == 1 && T >= 1024) ? 1 : 0;
   if (p.use_pair) p.num_m_blocks = (p.M + 255) / 256;
   p.group_m = gemm::choose_group_m(K, p.use_pair ? 256 : gemm::BM, p.num_m_blocks);
+  {
+    // B200_GEMM_L2_HINTS = three digits for (A, B, C): 0 normal, 1 evict-first, 2 evict-last. Default "201".
+    // Measured (tests/gemm_l2_probe.py under ncu, C3 up+gate GEMM, 4096-row groups): DRAM reads 3.57 GB with no hints,
+    // 3.41 GB with 201, 7.2 GB with evict-first weights (a weight slab IS re-read by the other CTAs of its wave, with skew);
+    // SM cycles are the same for all of them (5.05-5.09 M: the kernel is tensor-bound) but under the power cap less DRAM
+    // traffic means a higher clock: 3.83 ms at 3.6 GB vs 4.20 ms at 10.3 GB (1024-row groups).
+    static const uint64_t enc[3] = {kL2EvictNormal, kL2EvictFirst, kL2EvictLast};
+    const char* e = getenv("B200_GEMM_L2_HINTS");
+    int d[3] = {2, 0, 1};
+    if (e != nullptr && e[0] && e[1] && e[2])
+      for (int q = 0; q < 3; ++q) d[q] = (e[q] >= '0' && e[q] <= '2') ? e[q] - '0' : 0;
+    p.hint_a = enc[d[0]]; p.hint_b = enc[d[1]]; p.hint_c = enc[d[2]];
+  }
   p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
   p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.num_tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;

@@ -7,6 +7,8 @@
 // variance like the reference's (x - u)^2 mean, not E[x^2] - u^2), block reduction by warp shuffles + shared memory.
 // Algorithmic bytes per row: cols * 2 * (2 + has_residual).
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_common.h"
 
@@ -108,28 +110,44 @@ constexpr int W_MAX_ITERS_LIMIT = 8;  // warp-per-row kernel: cols <= 32 * VEC *
 // ITERS = ceil(cols / 256) is a template parameter: the row lives in ITERS*8 registers per lane, so narrow rows (768
 // columns: 24 registers) leave room for 5+ resident CTAs per SM instead of the 2 a worst-case 2048-column row buffer
 // allows — the kernel is HBM-bound and needs the bytes in flight. The grid is persistent (warps stride over the rows).
-template <typename T, bool HAS_RES, int ITERS>
+template <typename T, bool HAS_RES, int ITERS, bool PREFETCH>
 __global__ void __launch_bounds__(THREADS)
 layernorm_warp_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, const T* __restrict__ b,
                       T* __restrict__ y, int64_t rows, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps,
                       float alpha) {
   constexpr int W_MAX_ITERS = ITERS;
+  // Software pipelining across rows: the 128-bit loads of the warp's NEXT row are issued as soon as the current row has
+  // been unpacked to fp32, so they are in flight during the two shuffle reductions and the stores (narrow rows only: the
+  // staging registers cost 4 * ITERS (8 with a residual) per lane).
+  constexpr bool kPrefetch = PREFETCH && ITERS <= 4;
   const int lane = threadIdx.x & 31;
   const int64_t warps_total = static_cast<int64_t>(gridDim.x) * (THREADS / 32);
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5); row < rows; row += warps_total) {
-  const T* xr = x + row * ldx;
-  const T* rr = HAS_RES ? res + row * ldr : nullptr;
+  uint4 nx[W_MAX_ITERS], nr[W_MAX_ITERS];
+  auto load_row = [&](int64_t r) {
+#pragma unroll
+    for (int it = 0; it < W_MAX_ITERS; ++it) {
+      const int c = (it * 32 + lane) * VEC;
+      if (c < cols) {
+        nx[it] = *reinterpret_cast<const uint4*>(x + r * ldx + c);
+        if constexpr (HAS_RES) nr[it] = *reinterpret_cast<const uint4*>(res + r * ldr + c);
+      }
+    }
+  };
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * (THREADS / 32) + (threadIdx.x >> 5);
+  if (kPrefetch && row0 < rows) load_row(row0);
+  for (int64_t row = row0; row < rows; row += warps_total) {
+  if (!kPrefetch) load_row(row);
   float v[W_MAX_ITERS][VEC];
   float sum = 0.f;
 #pragma unroll
   for (int it = 0; it < W_MAX_ITERS; ++it) {
     const int c = (it * 32 + lane) * VEC;
     if (c < cols) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
+      const uint4 raw = nx[it];
       const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
       uint32_t rs[4] = {0, 0, 0, 0};
       if constexpr (HAS_RES) {
-        const uint4 r4 = *reinterpret_cast<const uint4*>(rr + c);
+        const uint4 r4 = nr[it];
         rs[0] = r4.x; rs[1] = r4.y; rs[2] = r4.z; rs[3] = r4.w;
       }
 #pragma unroll
@@ -150,6 +168,7 @@ layernorm_warp_kernel(const T* __restrict__ x, const T* __restrict__ res, const 
       for (int e = 0; e < VEC; ++e) v[it][e] = 0.f;
     }
   }
+  if (kPrefetch && row + warps_total < rows) load_row(row + warps_total);
 #pragma unroll
   for (int xo = 16; xo >= 1; xo >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, xo);
   const float mean = sum / static_cast<float>(cols);
@@ -212,13 +231,20 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
   const int w_iters = (cols + 32 * ln::VEC - 1) / (32 * ln::VEC);
   const int64_t warp_ctas = (rows + ln::THREADS / 32 - 1) / (ln::THREADS / 32);
   const int64_t resident = static_cast<int64_t>(sm_count()) * 8;  // persistent: at most 8 CTAs of 256 threads per SM
+  const char* pf_env = getenv("B200_LN_PREFETCH");
+  const bool prefetch = !(pf_env && pf_env[0] == '0');
   const unsigned grid = narrow ? static_cast<unsigned>(warp_ctas < resident ? warp_ctas : resident)
                                : static_cast<unsigned>(rows);
 #define LAUNCH_W(T, HAS, IT)                                                                                       \
   case IT:                                                                                                             \
-    ln::layernorm_warp_kernel<T, HAS, IT><<<grid, ln::THREADS, 0, s>>>(                                                \
-        static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
-        static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);              \
+    if (prefetch)                                                                                                    \
+      ln::layernorm_warp_kernel<T, HAS, IT, true><<<grid, ln::THREADS, 0, s>>>(                                        \
+          static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                    \
+          static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);            \
+    else                                                                                                             \
+      ln::layernorm_warp_kernel<T, HAS, IT, false><<<grid, ln::THREADS, 0, s>>>(                                       \
+          static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                    \
+          static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);            \
     break;
 #define LAUNCH(T, HAS)                                                                                              \
   if (narrow) {                                                                                                        \

@@ -297,20 +297,36 @@ def kv_append(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor, v_c
               context_lens: torch.Tensor, block_tables: Optional[torch.Tensor] = None, layer_idx: int = 0) -> None:
     """Write the new token's K,V ``[B,Hkv,D]`` into the cache at position ``context_lens[b]-1``."""
     dev = _require_cuda(key, value, k_cache, v_cache, context_lens, block_tables)
+    if key.dim() != 3 or value.shape != key.shape:
+        raise ValueError(f"key / value must be [B,Hkv,D], got {tuple(key.shape)}, {tuple(value.shape)}")
     B, Hkv, D = key.shape
+    _dtype_code(key)
+    if value.dtype != key.dtype or k_cache.dtype != key.dtype or v_cache.dtype != key.dtype:
+        raise ValueError("key, value and both caches must share a dtype")
+    if context_lens.dtype != torch.int32 or not context_lens.is_contiguous() or context_lens.numel() != B:
+        raise ValueError("context_lens must be a contiguous int32 [B] tensor")
     key, value = key.contiguous(), value.contiguous()
     paged = block_tables is not None
     if paged:
-        if not k_cache.is_contiguous() or not v_cache.is_contiguous() or k_cache.dim() != 5:
+        if not k_cache.is_contiguous() or not v_cache.is_contiguous() or k_cache.dim() != 5 or v_cache.shape != k_cache.shape:
             raise ValueError("paged cache must be contiguous [num_blocks, L, block_size, Hkv, D]")
-        _, num_layers, block_size, _, _ = k_cache.shape
+        _, num_layers, block_size, Hc, Dc = k_cache.shape
+        if block_tables.dtype != torch.int32 or block_tables.dim() != 2 or block_tables.shape[0] != B or \
+                not block_tables.is_contiguous():
+            raise ValueError("block_tables must be a contiguous int32 [B, max_blocks] tensor")
+        if not 0 <= int(layer_idx) < num_layers:
+            raise ValueError(f"layer_idx {layer_idx} outside the cache's {num_layers} layers")
         max_blocks = block_tables.shape[1]
         kv_bs = kv_ts = 0
     else:
-        if k_cache.dim() != 4 or k_cache.stride(-1) != 1 or k_cache.stride(2) != D:
-            raise ValueError("contiguous cache must be [B,S_max,Hkv,D] with (Hkv, D) dense")
+        if k_cache.dim() != 4 or k_cache.stride(-1) != 1 or k_cache.stride(2) != D or v_cache.shape != k_cache.shape or \
+                v_cache.stride() != k_cache.stride() or k_cache.shape[0] < B:
+            raise ValueError("contiguous cache must be [B,S_max,Hkv,D] with (Hkv, D) dense, k and v alike")
+        Hc, Dc = k_cache.shape[2], k_cache.shape[3]
         kv_bs, kv_ts = k_cache.stride(0), k_cache.stride(1)
-        num_layers, block_size, max_blocks = 1, 0, 0
+        num_layers, block_size, max_blocks = 1, 0, k_cache.shape[1]  # contiguous: the capacity S_max travels in max_blocks
+    if (Hc, Dc) != (Hkv, D):
+        raise ValueError(f"cache heads / head_dim {(Hc, Dc)} do not match key {(Hkv, D)}")
     lib = _lib.load()
     with torch.cuda.device(dev):
         rc = lib.b200_kv_append(key.data_ptr(), value.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), B, Hkv, D,

@@ -7,7 +7,8 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for rows, cols in ((32768, 768), (32768, 1024), (32768, 2048), (32768, 4096), (32768, 8192)):
     x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16); r = torch.randn_like(x)
     w = torch.randn(cols, device="cuda", dtype=torch.bfloat16); b = torch.randn_like(w)
-    for res in (None, r):
+    for res, pf in ((None, "1"), (None, "0"), (r, "1"), (r, "0")):
+        os.environ["B200_LN_PREFETCH"] = pf
         ts = []
         for _ in range(12):
             flush.zero_()
@@ -16,4 +17,4 @@ for rows, cols in ((32768, 768), (32768, 1024), (32768, 2048), (32768, 4096), (3
             ts.append(s.elapsed_time(e))
         ms = sorted(ts)[len(ts) // 2]
         nbytes = rows * cols * 2 * (2 + (res is not None))
-        print(f"LN rows={rows} cols={cols} residual={res is not None}: {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s", flush=True)
+        print(f"LN rows={rows} cols={cols} residual={res is not None} prefetch={pf}: {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s", flush=True)

@@ -303,6 +303,32 @@ def test_paged_short_q_attention_vs_oracle(ops, Sq, Hq, Hkv, D, block_size, caus
         assert (od.float() - o[:, -1].float()).abs().max().item() <= 2e-2
 
 
+def test_kv_append_and_decode_clamp_overlong_lengths(ops):
+    """device-side lengths past the cache capacity (e.g. advanced under a CUDA graph) must neither write into
+    another sequence's block nor read past the block table."""
+    B, Hkv, D, bs, nblk = 2, 2, 64, 16, 3
+    kc = torch.zeros(B * nblk, 1, bs, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    bt = torch.arange(B * nblk, dtype=torch.int32, device="cuda").view(B, nblk)
+    k = torch.ones(B, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    lens = torch.tensor([nblk * bs + 5, 7], device="cuda", dtype=torch.int32)   # sequence 0 ran past its 48 slots
+    ops.kv_append(k, k, kc, vc, lens, bt, 0)
+    assert kc[:nblk].abs().sum().item() == 0 and kc[nblk:].abs().sum().item() == Hkv * D   # only sequence 1's token landed
+    assert kc[nblk, 0, 6].abs().sum().item() == Hkv * D
+    q = torch.randn(B, 4, D, device="cuda", dtype=torch.bfloat16)
+    o = ops.decode_attention(q, kc, vc, lens, block_tables=bt)                 # clamped to 48 keys: finite, no fault
+    torch.cuda.synchronize()
+    assert torch.isfinite(o.float()).all()
+    kcc = torch.zeros(B, 8, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    lens2 = torch.tensor([9, 8], device="cuda", dtype=torch.int32)             # contiguous cache of 8 slots
+    ops.kv_append(k, k, kcc, kcc.clone(), lens2)
+    assert kcc[0].abs().sum().item() == 0 and kcc[1, 7].abs().sum().item() == Hkv * D
+    with pytest.raises(ValueError):
+        ops.kv_append(k, k, kc, vc, lens.long(), bt, 0)
+    with pytest.raises(ValueError):
+        ops.kv_append(k, k, kc, vc, lens, bt[:1], 0)
+
+
 def test_decode_equals_last_prefill_row(ops):
     B, S, Hq, Hkv, D = 2, 1024, 8, 2, 128
     q, k, v = rand_qkv(B, S, S, Hq, Hkv, D, seed=3)
