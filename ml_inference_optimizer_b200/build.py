@@ -38,18 +38,36 @@ def _existing_sources() -> list[Path]:
     return [CSRC / s for s in SOURCES if (CSRC / s).exists()]
 
 
+STAMP_PATH = PKG_DIR / "build" / "source_stamp.txt"
+
+
+def source_stamp() -> str:
+    """SHA-256 over every source, header and the compiler flags: what the library on disk must have been built from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + os.environ.get("B200_EXTRA_NVCC_FLAGS", "").split()).encode())
+    for d in _existing_sources() + [(CSRC / x).resolve() for x in HEADERS]:
+        if d.exists():
+            h.update(d.name.encode())
+            h.update(d.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not LIB_PATH.exists():
+    """True unless the library exists AND was built from exactly the current sources (content hash, not mtime: a
+    checkout or a snapshot copy resets mtimes, and a prebuilt .so must never mask a source change)."""
+    if not LIB_PATH.exists() or not STAMP_PATH.exists():
         return True
-    lib_mtime = LIB_PATH.stat().st_mtime
-    deps = _existing_sources() + [(CSRC / h).resolve() for h in HEADERS]
-    return any(d.exists() and d.stat().st_mtime > lib_mtime for d in deps)
+    return STAMP_PATH.read_text().strip() != source_stamp()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
+    force = force or os.environ.get("B200_FORCE_REBUILD", "") not in ("", "0")
     if not force and not needs_build():
         return LIB_PATH
+    stamp = source_stamp()
     nvcc = _nvcc()
     obj_dir = PKG_DIR / "build"
     obj_dir.mkdir(exist_ok=True)
@@ -74,6 +92,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}")
     os.replace(tmp, LIB_PATH)
+    STAMP_PATH.write_text(stamp + "\n")
     return LIB_PATH
 
 

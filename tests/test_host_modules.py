@@ -35,8 +35,11 @@ def test_signatures_match_reference_appendix_a():
         "self", "use_flash_attention", "use_fused_mlp", "tensor_parallel_size"]
     assert list(inspect.signature(RingAttentionConfig).parameters)[:4] == ["world_size", "chunk_size", "fuse_qkv", "use_flash_attention"]
     from kernels.triton.attention_kernels import triton_paged_attention_forward, triton_reshape_and_cache
-    assert list(inspect.signature(triton_paged_attention_forward).parameters) == [
+    paged = inspect.signature(triton_paged_attention_forward).parameters
+    assert list(paged)[:9] == [
         "query", "output", "k_cache", "v_cache", "block_tables", "context_lengths", "block_size", "max_seq_len", "layer_idx"]
+    # anything past the reference's arguments (the short-q `causal` switch) must be optional
+    assert all(p.default is not inspect.Parameter.empty for p in list(paged.values())[9:])
     assert list(inspect.signature(triton_reshape_and_cache).parameters) == [
         "key", "value", "k_cache", "v_cache", "block_tables", "context_lengths", "layer_idx"]
     from kernels.triton.mlp_kernels import triton_fused_mlp
