@@ -2,9 +2,10 @@
 // (SURVEY.md §8 f3). Replaces _layernorm_fwd_kernel / _layernorm_residual_fwd_kernel / triton_layernorm
 // (kernels/triton/layernorm_kernels.py:36-190, :191-277).
 //
-// HBM-bound: each element is read once (x, and the residual when present) and written once. One CTA of 256 threads
-// per row; 128-bit loads, the row is held in fp32 registers between the mean pass and the variance pass (two-pass
-// variance like the reference's (x - u)^2 mean, not E[x^2] - u^2), block reduction by warp shuffles + shared memory.
+// HBM-bound: each element is read once (x, and the residual when present) and written once. One warp (<= 2048 columns)
+// or one CTA of 256 threads (<= 8192) per row, both persistent with the next row's 128-bit loads in flight; the row is
+// held in fp32 registers between the mean pass and the variance pass (two-pass variance like the reference's
+// (x - u)^2 mean, not E[x^2] - u^2).
 // Algorithmic bytes per row: cols * 2 * (2 + has_residual).
 
 #include <stdlib.h>
@@ -19,87 +20,112 @@ constexpr int THREADS = 256;
 constexpr int VEC = 8;         // 16-bit elements per 128-bit access
 constexpr int MAX_ITERS = 4;   // cols <= THREADS * VEC * MAX_ITERS = 8192
 
+// streaming 128-bit load: the activations are read exactly once, so they bypass L1 allocation
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// Block-wide sum; `red` is one of two alternating 8-float buffers, so a single __syncthreads per reduction is enough:
+// buffer A is only rewritten after every thread has passed the barrier of the following reduction on buffer B.
 __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
   for (int x = 16; x >= 1; x >>= 1) v += __shfl_xor_sync(0xffffffffu, v, x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();  // protects `red` between consecutive reductions
   if (lane == 0) red[warp] = v;
   __syncthreads();
-  float t = (lane < THREADS / 32) ? red[lane] : 0.f;
+  float t = red[lane & (THREADS / 32 - 1)];
 #pragma unroll
   for (int x = 4; x >= 1; x >>= 1) t += __shfl_xor_sync(0xffffffffu, t, x);
-  return __shfl_sync(0xffffffffu, t, 0);
+  return t;
 }
 
-template <typename T, bool HAS_RES>
+// wide rows (2048 < cols <= 8192): one CTA per row at a time, persistent over the rows (grid = resident CTAs), ITERS =
+// ceil(cols / 2048) 128-bit loads per thread and operand. The loads of the CTA's NEXT row are issued before the two
+// block reductions of the current one, so every CTA keeps a full row in flight while it reduces, normalises and
+// stores (a CTA that exits per row has nothing in flight during those phases: 0.60-0.68 of copy bandwidth at 4096
+// columns). weight / bias are re-read from L1/L2 per row (8-16 KB, shared by every row).
+template <typename T, bool HAS_RES, int ITERS>
 __global__ void __launch_bounds__(THREADS)
 layernorm_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ w, const T* __restrict__ b,
-                 T* __restrict__ y, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps, float alpha) {
-  __shared__ float red[THREADS / 32];
-  const int64_t row = blockIdx.x;
-  const T* xr = x + row * ldx;
-  const T* rr = HAS_RES ? res + row * ldr : nullptr;
-  float v[MAX_ITERS][VEC];
-  float sum = 0.f;
+                 T* __restrict__ y, int64_t rows, int cols, int64_t ldx, int64_t ldr, int64_t ldy, float eps, float alpha) {
+  __shared__ float red[2][THREADS / 32];
+  uint4 nx[ITERS], nr[ITERS];
+  auto load_row = [&](int64_t r) {
 #pragma unroll
-  for (int it = 0; it < MAX_ITERS; ++it) {
-    const int c = (it * THREADS + threadIdx.x) * VEC;
-    if (c < cols) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c);
-      float2 f;
-      f = Pack2<T>::unpack(raw.x); v[it][0] = f.x; v[it][1] = f.y;
-      f = Pack2<T>::unpack(raw.y); v[it][2] = f.x; v[it][3] = f.y;
-      f = Pack2<T>::unpack(raw.z); v[it][4] = f.x; v[it][5] = f.y;
-      f = Pack2<T>::unpack(raw.w); v[it][6] = f.x; v[it][7] = f.y;
-      if constexpr (HAS_RES) {
-        const uint4 rw = *reinterpret_cast<const uint4*>(rr + c);
-        f = Pack2<T>::unpack(rw.x); v[it][0] = fmaf(alpha, f.x, v[it][0]); v[it][1] = fmaf(alpha, f.y, v[it][1]);
-        f = Pack2<T>::unpack(rw.y); v[it][2] = fmaf(alpha, f.x, v[it][2]); v[it][3] = fmaf(alpha, f.y, v[it][3]);
-        f = Pack2<T>::unpack(rw.z); v[it][4] = fmaf(alpha, f.x, v[it][4]); v[it][5] = fmaf(alpha, f.y, v[it][5]);
-        f = Pack2<T>::unpack(rw.w); v[it][6] = fmaf(alpha, f.x, v[it][6]); v[it][7] = fmaf(alpha, f.y, v[it][7]);
-      }
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) sum += v[it][e];
-    } else {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) v[it][e] = 0.f;
-    }
-  }
-  const float mean = block_sum(sum, red) / static_cast<float>(cols);
-  float sq = 0.f;
-#pragma unroll
-  for (int it = 0; it < MAX_ITERS; ++it) {
-    const int c = (it * THREADS + threadIdx.x) * VEC;
-    if (c < cols) {
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        const float d = v[it][e] - mean;
-        sq = fmaf(d, d, sq);
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * THREADS + threadIdx.x) * VEC;
+      if (c < cols) {
+        nx[it] = ld_stream(x + r * ldx + c);
+        if constexpr (HAS_RES) nr[it] = ld_stream(res + r * ldr + c);
       }
     }
-  }
-  const float rstd = rsqrtf(block_sum(sq, red) / static_cast<float>(cols) + eps);
-  T* yr = y + row * ldy;
+  };
+  int64_t row = blockIdx.x;
+  if (row < rows) load_row(row);
+  for (; row < rows; row += gridDim.x) {
+    float v[ITERS][VEC];
+    float sum = 0.f;
 #pragma unroll
-  for (int it = 0; it < MAX_ITERS; ++it) {
-    const int c = (it * THREADS + threadIdx.x) * VEC;
-    if (c < cols) {
-      const uint4 wr = __ldg(reinterpret_cast<const uint4*>(w + c));
-      uint4 br = make_uint4(0, 0, 0, 0);
-      if (b != nullptr) br = __ldg(reinterpret_cast<const uint4*>(b + c));
-      float o[VEC];
-      const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w}, bb[4] = {br.x, br.y, br.z, br.w};
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * THREADS + threadIdx.x) * VEC;
+      if (c < cols) {
+        const uint32_t rw[4] = {nx[it].x, nx[it].y, nx[it].z, nx[it].w};
+        uint32_t rs[4] = {0, 0, 0, 0};
+        if constexpr (HAS_RES) { rs[0] = nr[it].x; rs[1] = nr[it].y; rs[2] = nr[it].z; rs[3] = nr[it].w; }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 wf = Pack2<T>::unpack(ww[q]), bf = Pack2<T>::unpack(bb[q]);
-        o[2 * q] = fmaf((v[it][2 * q] - mean) * rstd, wf.x, bf.x);
-        o[2 * q + 1] = fmaf((v[it][2 * q + 1] - mean) * rstd, wf.y, bf.y);
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = Pack2<T>::unpack(rw[q]);
+          v[it][2 * q] = f.x;
+          v[it][2 * q + 1] = f.y;
+          if constexpr (HAS_RES) {
+            const float2 g = Pack2<T>::unpack(rs[q]);
+            v[it][2 * q] = fmaf(alpha, g.x, v[it][2 * q]);
+            v[it][2 * q + 1] = fmaf(alpha, g.y, v[it][2 * q + 1]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) sum += v[it][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[it][e] = 0.f;
       }
-      uint4 pk;
-      pk.x = Pack2<T>::pack(o[0], o[1]); pk.y = Pack2<T>::pack(o[2], o[3]);
-      pk.z = Pack2<T>::pack(o[4], o[5]); pk.w = Pack2<T>::pack(o[6], o[7]);
-      *reinterpret_cast<uint4*>(yr + c) = pk;
+    }
+    if (row + gridDim.x < rows) load_row(row + gridDim.x);
+    const float mean = block_sum(sum, red[0]) / static_cast<float>(cols);
+    float sq = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if ((it * THREADS + threadIdx.x) * VEC < cols) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          const float d = v[it][e] - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+    }
+    const float rstd = rsqrtf(block_sum(sq, red[1]) / static_cast<float>(cols) + eps);
+    T* yr = y + row * ldy;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * THREADS + threadIdx.x) * VEC;
+      if (c < cols) {
+        const uint4 wr = __ldg(reinterpret_cast<const uint4*>(w + c));
+        uint4 br = make_uint4(0, 0, 0, 0);
+        if (b != nullptr) br = __ldg(reinterpret_cast<const uint4*>(b + c));
+        const uint32_t ww[4] = {wr.x, wr.y, wr.z, wr.w}, bb[4] = {br.x, br.y, br.z, br.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 wf = Pack2<T>::unpack(ww[q]), bf = Pack2<T>::unpack(bb[q]);
+          pk[q] = Pack2<T>::pack(fmaf((v[it][2 * q] - mean) * rstd, wf.x, bf.x),
+                                 fmaf((v[it][2 * q + 1] - mean) * rstd, wf.y, bf.y));
+        }
+        *reinterpret_cast<uint4*>(yr + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
     }
   }
 }
@@ -227,14 +253,24 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "layernorm: dtype must be bf16 or fp16");
   if (rows == 0) return B200_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool narrow = cols <= 32 * ln::VEC * ln::W_MAX_ITERS_LIMIT;
+  // B200_LN_NARROW_MAX (developer knob): widest row the warp-per-row kernel takes
+  const char* nm_env = getenv("B200_LN_NARROW_MAX");
+  // measured (T = 32768 rows, profiles/r2_ln_probe2.log): up to 1024 columns the warp kernel (its next-row prefetch needs
+  // ITERS <= 4) wins; at 2048 columns the CTA kernel wins with a residual (5172 vs 4012 GB/s) and loses without one
+  // (3857 vs 4443 GB/s)
+  const int narrow_dflt = residual ? 1024 : 32 * ln::VEC * ln::W_MAX_ITERS_LIMIT;
+  const int narrow_max = (nm_env && atoi(nm_env) > 0) ? min(atoi(nm_env), 32 * ln::VEC * ln::W_MAX_ITERS_LIMIT) : narrow_dflt;
+  const bool narrow = cols <= narrow_max;
   const int w_iters = (cols + 32 * ln::VEC - 1) / (32 * ln::VEC);
   const int64_t warp_ctas = (rows + ln::THREADS / 32 - 1) / (ln::THREADS / 32);
   const int64_t resident = static_cast<int64_t>(sm_count()) * 8;  // persistent: at most 8 CTAs of 256 threads per SM
   const char* pf_env = getenv("B200_LN_PREFETCH");
   const bool prefetch = !(pf_env && pf_env[0] == '0');
-  const unsigned grid = narrow ? static_cast<unsigned>(warp_ctas < resident ? warp_ctas : resident)
-                               : static_cast<unsigned>(rows);
+  const int wide_iters = (cols + ln::THREADS * ln::VEC - 1) / (ln::THREADS * ln::VEC);  // 2..4 for 2048 < cols <= 8192
+  // wide rows: persistent as well; B200_LN_WIDE_CTAS_PER_SM (developer knob) overrides the resident CTAs per SM
+  const char* wc_env = getenv("B200_LN_WIDE_CTAS_PER_SM");
+  const int wide_per_sm = (wc_env && atoi(wc_env) > 0) ? atoi(wc_env) : 0;  // 0: as many as fit
+  const unsigned grid = static_cast<unsigned>(warp_ctas < resident ? warp_ctas : resident);  // (narrow kernel)
 #define LAUNCH_W(T, HAS, IT)                                                                                       \
   case IT:                                                                                                             \
     if (prefetch)                                                                                                    \
@@ -246,6 +282,18 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
           static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                    \
           static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);            \
     break;
+#define LAUNCH_C(T, HAS, IT)                                                                                       \
+  case IT: {                                                                                                           \
+    static int occ = 0; /* resident CTAs per SM of this instantiation (register-limited: 2 at 8192 columns + residual) */ \
+    if (occ == 0) {                                                                                                    \
+      B200_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ln::layernorm_kernel<T, HAS, IT>, ln::THREADS, 0)); \
+      if (occ < 1) occ = 1;                                                                                            \
+    }                                                                                                                  \
+    const int64_t res_w = static_cast<int64_t>(sm_count()) * (wide_per_sm > 0 && wide_per_sm < occ ? wide_per_sm : occ); \
+    ln::layernorm_kernel<T, HAS, IT><<<static_cast<unsigned>(rows < res_w ? rows : res_w), ln::THREADS, 0, s>>>(       \
+        static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
+        static_cast<const T*>(bias), static_cast<T*>(y), rows, cols, ldx, ldr, ldy, eps, residual_alpha);              \
+  } break;
 #define LAUNCH(T, HAS)                                                                                              \
   if (narrow) {                                                                                                        \
     switch (w_iters) {                                                                                                 \
@@ -253,10 +301,12 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
       LAUNCH_W(T, HAS, 6) LAUNCH_W(T, HAS, 7) LAUNCH_W(T, HAS, 8)                                                      \
       default: break;                                                                                                  \
     }                                                                                                                  \
-  } else                                                                                                                 \
-    ln::layernorm_kernel<T, HAS><<<grid, ln::THREADS, 0, s>>>(                                                        \
-        static_cast<const T*>(x), static_cast<const T*>(residual), static_cast<const T*>(weight),                      \
-        static_cast<const T*>(bias), static_cast<T*>(y), cols, ldx, ldr, ldy, eps, residual_alpha)
+  } else {                                                                                                               \
+    switch (wide_iters) {                                                                                              \
+      LAUNCH_C(T, HAS, 1) LAUNCH_C(T, HAS, 2) LAUNCH_C(T, HAS, 3) LAUNCH_C(T, HAS, 4)                                                   \
+      default: break;                                                                                                  \
+    }                                                                                                                  \
+  }
   if (dtype == B200_DTYPE_BF16) {
     if (residual) { LAUNCH(__nv_bfloat16, true); } else { LAUNCH(__nv_bfloat16, false); }
   } else {
@@ -264,6 +314,7 @@ extern "C" int b200_layernorm(const void* x, const void* residual, const void* w
   }
 #undef LAUNCH
 #undef LAUNCH_W
+#undef LAUNCH_C
   B200_CUDA_OK(cudaGetLastError());
   note_launch("layernorm_kernel");
   return B200_OK;

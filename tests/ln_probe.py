@@ -7,8 +7,13 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for rows, cols in ((32768, 768), (32768, 1024), (32768, 2048), (32768, 4096), (32768, 8192)):
     x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16); r = torch.randn_like(x)
     w = torch.randn(cols, device="cuda", dtype=torch.bfloat16); b = torch.randn_like(w)
-    for res, pf in ((None, "1"), (None, "0"), (r, "1"), (r, "0")):
+    variants = [(None, "1", "", ""), (r, "1", "", "")]
+    if cols > 1024:
+        variants += [(rr, "1", nm, pc) for rr in (None, r) for nm in (["512"] if cols <= 2048 else [""]) for pc in ("", "2", "3", "4")]
+    for res, pf, nm, pc in variants:
         os.environ["B200_LN_PREFETCH"] = pf
+        os.environ["B200_LN_NARROW_MAX"] = nm
+        os.environ["B200_LN_WIDE_CTAS_PER_SM"] = pc
         ts = []
         for _ in range(12):
             flush.zero_()
@@ -17,4 +22,4 @@ for rows, cols in ((32768, 768), (32768, 1024), (32768, 2048), (32768, 4096), (3
             ts.append(s.elapsed_time(e))
         ms = sorted(ts)[len(ts) // 2]
         nbytes = rows * cols * 2 * (2 + (res is not None))
-        print(f"LN rows={rows} cols={cols} residual={res is not None} prefetch={pf}: {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s", flush=True)
+        print(f"LN rows={rows} cols={cols} residual={res is not None} prefetch={pf} narrow_max={nm or "dflt"} wide_ctas={pc or "occ"}: {ms*1e3:7.1f} us  {nbytes/ms/1e6:7.0f} GB/s", flush=True)

@@ -11,7 +11,16 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.max",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed",
+        "smsp__inst_executed_pipe_xu.sum", "smsp__inst_executed_pipe_fma.sum", "smsp__inst_executed_pipe_alu.sum",
+        "smsp__inst_executed_pipe_fmaheavy.sum", "smsp__inst_executed_pipe_fmalite.sum",
+        "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warp_latency_per_inst_issued.ratio"]
 
 
 def main(path):
@@ -32,8 +41,10 @@ def main(path):
         stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
         data = [r for r in rows[2:] if len(r) == len(hdr)]
         tot = sum(int(r[isamp] or 0) for r in data)
+        agg = sorted(((sum(int(r[i] or 0) for r in data), hdr[i]) for i in stall), reverse=True)
+        print("  stall reasons (all instructions): " + ", ".join(f"{h}={n} ({100.0 * n / max(tot, 1):.1f}%)" for n, h in agg[:10]))
         print(f"  warp-stall samples: {tot}; top instructions:")
-        for r in sorted(data, key=lambda r: -int(r[isamp] or 0))[:12]:
+        for r in sorted(data, key=lambda r: -int(r[isamp] or 0))[:int(__import__('os').environ.get('NCU_TOP', '12'))]:
             st = sorted(((int(r[i] or 0), hdr[i]) for i in stall), reverse=True)[:2]
             print(f"    {int(r[isamp]):7d} ({100.0 * int(r[isamp]) / max(tot, 1):4.1f}%)  {r[isrc][:64]:64s} {st}")
 

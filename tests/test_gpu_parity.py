@@ -491,7 +491,12 @@ def test_mlp_full_size_linearity(ops):
 
 # ------------------------------------------------------------------------------------------ LayerNorm (f3)
 @pytest.mark.parametrize("rows,cols,res,bias", [(300, 768, False, True), (257, 4096, True, True), (5, 8192, True, False),
-                                                (1, 64, False, True), (1000, 1032, True, True)])
+                                                (1, 64, False, True), (1000, 1032, True, True),
+                                                # persistent CTA-per-row kernel: more rows than resident CTAs (several
+                                                # rows per CTA with the next row prefetched), every ITERS instantiation,
+                                                # ragged widths, with and without residual
+                                                (3001, 2048, True, True), (2500, 2056, False, False), (1777, 4104, True, True),
+                                                (1300, 6152, False, True), (1201, 8192, False, True), (700, 3000, True, False)])
 def test_layernorm_vs_oracle(ops, rows, cols, res, bias):
     g = torch.Generator(device="cuda").manual_seed(3)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g).to(torch.bfloat16)
