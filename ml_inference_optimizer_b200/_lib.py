@@ -6,7 +6,9 @@ every compute entry point fails with ``B200Error`` when no sm_100 device is pres
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
+from pathlib import Path
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p, POINTER
 
 from .build import LIB_PATH
@@ -79,12 +81,15 @@ def load() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not LIB_PATH.exists():
+        path = LIB_PATH
+        if os.environ.get("B200_LIB_PATH"):  # developer A/B runs only: another build of the SAME library (tests/*_probe.py)
+            path = Path(os.environ["B200_LIB_PATH"]).resolve()
+        if not path.exists():
             raise RuntimeError(
-                f"{LIB_PATH} is missing: the sm_100a extension has not been built. Run "
+                f"{path} is missing: the sm_100a extension has not been built. Run "
                 "`python -c 'import __graft_entry__ as g; g.build()'` (or `python -m ml_inference_optimizer_b200.build`). "
                 "There is deliberately no CPU / PyTorch fallback for the attention + FusedMLP hot path.")
-        lib = ctypes.CDLL(str(LIB_PATH))
+        lib = ctypes.CDLL(str(path))
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the header and the library disagree
             fn.restype = restype

@@ -279,9 +279,12 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 }
 
 constexpr int GQA_WARPS = 4;
+// resident CTAs per SM the register allocation is capped for: two tiles of K/V are staged in registers per lane
+// (D = 128: 128 of ~250 registers -> 2 CTAs; D = 64: 64 of ~170 -> 3 CTAs, measured 4721 vs 4002 GB/s with 2)
+template <int D> struct GqaMinCtas { static constexpr int value = D == 128 ? 2 : 3; };
 
 template <int D, typename T, bool PAGED>
-__global__ void __launch_bounds__(GQA_WARPS * 32, 3)
+__global__ void __launch_bounds__(GQA_WARPS * 32, GqaMinCtas<D>::value)
 decode_gqa_mma_kernel(const Params p, const int G) {
   constexpr int TILE = 16;       // keys per warp iteration
   constexpr int MB = D / 32;     // 32-dim blocks of the head dimension (two MMA k-steps each)
@@ -330,9 +333,11 @@ decode_gqa_mma_kernel(const Params p, const int G) {
     }
   };
 
-  for (int t0 = k_begin + warp * TILE; t0 < k_end; t0 += GQA_WARPS * TILE) {
-    // ---- issue every load of the tile ----
-    uint4 kr[2][MB], vr[DG][4];
+  // Software pipeline over the warp's tiles: the 16 128-bit loads of tile i+1 are issued BEFORE the MMAs / softmax of
+  // tile i, so every warp always has a full tile (8 KB) in flight instead of only during its load phase (the kernel is
+  // HBM-bound: 67.8 % of DRAM peak without the prefetch, profiles/r1_decode_v1_ncu.txt). Two register buffers, loop
+  // unrolled by two so their roles are static.
+  auto issue_tile = [&](const int t0, uint4 (&kr)[2][MB], uint4 (&vr)[DG][4]) {
 #pragma unroll
     for (int kg = 0; kg < 2; ++kg) {
       const int key = t0 + kg * 8 + g;
@@ -349,6 +354,8 @@ decode_gqa_mma_kernel(const Params p, const int G) {
 #pragma unroll
       for (int d = 0; d < DG; ++d) vr[d][j] = valid ? ld_stream(vc + off + 64 * d) : make_uint4(0, 0, 0, 0);
     }
+  };
+  auto compute_tile = [&](const int t0, const uint4 (&kr)[2][MB], const uint4 (&vr)[DG][4]) {
     // ---- S = Q K^T (rows g, g+8; keys kg*8 + 2t, +1) ----
     float sc[2][4];
 #pragma unroll
@@ -403,6 +410,16 @@ decode_gqa_mma_kernel(const Params p, const int G) {
         mma_16816<T>(o[d * 8 + j], pa0, pa1, pa2, pa3, b0, b1);
       }
     }
+  };
+  constexpr int STEP = GQA_WARPS * TILE;
+  uint4 krA[2][MB], vrA[DG][4], krB[2][MB], vrB[DG][4];
+  int t0 = k_begin + warp * TILE;
+  if (t0 < k_end) issue_tile(t0, krA, vrA);
+  for (; t0 < k_end; t0 += 2 * STEP) {
+    if (t0 + STEP < k_end) issue_tile(t0 + STEP, krB, vrB);
+    compute_tile(t0, krA, vrA);
+    if (t0 + 2 * STEP < k_end) issue_tile(t0 + 2 * STEP, krA, vrA);
+    if (t0 + STEP < k_end) compute_tile(t0 + STEP, krB, vrB);
   }
 
   // ---- combine: lanes of a row quad, then the warps of the CTA through shared memory ----

@@ -38,6 +38,12 @@ elif what in ("decode", "decode_gqa"):
     lens = torch.full((B,), S, device="cuda", dtype=torch.int32)
     for _ in range(reps):
         ops.decode_attention(q, kc, vc, lens)
+elif what == "ln":
+    x = torch.randn(32768, 4096, device="cuda", dtype=bf)
+    r = torch.randn_like(x)
+    w_, b_ = torch.randn(4096, device="cuda", dtype=bf), torch.randn(4096, device="cuda", dtype=bf)
+    for _ in range(reps):
+        ops.layernorm(x, w_, b_, 1e-5, residual=r)
 torch.cuda.synchronize()
 print("done", what)
 if what == "mlp64":
