@@ -70,10 +70,11 @@ int b200_set_sm_limit(int max_ctas);
 int b200_set_gemm_group_rows(int rows);
 
 /* Measurement hooks (the reference's BenchmarkRunner counts nothing, benchmarks/runners.py:185-248): number of kernel
- * launches this library has issued in the process so far, and the name of the GEMM kernel the last linear / FusedMLP
- * call dispatched to (static string). */
+ * launches this library has issued in the process so far, the name of the GEMM kernel the last linear / FusedMLP
+ * call dispatched to and the name of the kernel launched last, whatever it was (static strings). */
 int64_t b200_launch_count(void);
 const char* b200_last_gemm_kernel(void);
+const char* b200_last_kernel(void);
 
 /* ---- K1: tiled online-softmax attention forward (prefill) -------------------------------------------
  * Replaces triton_flash_attention / _flash_attention_forward_kernel

@@ -29,6 +29,7 @@ SIGNATURES = {
     "b200_set_gemm_group_rows": (c_int, [c_int]),
     "b200_launch_count": (c_int64, []),
     "b200_last_gemm_kernel": (c_char_p, []),
+    "b200_last_kernel": (c_char_p, []),
     "b200_fa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                             c_int64_p, c_int64_p, c_int64_p, c_int64_p, c_float, c_int, c_int64, c_void_p, c_int,
                             c_void_p]),

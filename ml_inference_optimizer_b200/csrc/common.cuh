@@ -339,6 +339,25 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
                "h"(cta_mask)
                : "memory");
 }
+// TMA load multicast to the CTAs of `cta_mask`: the box lands at the same shared-memory offset in each of them and each
+// CTA's mbarrier (same offset) receives the transaction bytes delivered to it
+__device__ __forceinline__ void tma_load_4d_mcast(void* smem_dst, const CUtensorMap* desc, uint64_t* bar, int c0, int c1, int c2,
+                                                  int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], %7;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit of a cta_group::1 MMA stream that arrives on the mbarrier at the same offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 // arrive on the mbarrier at the same offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   uint32_t remote;

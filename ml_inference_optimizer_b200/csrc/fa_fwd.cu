@@ -40,6 +40,7 @@ constexpr int BLOCK_N = 128;
 constexpr int NUM_THREADS = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
+constexpr bool kPairDefault = false;  // B200_FA_PAIR=1 selects the CTA-pair kernel (generation 3)
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8, safe for bf16/fp16 P and fp32 sums
 
 template <int D>
@@ -664,8 +665,503 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   return B200_OK;
 }
 
+// =====================================================================================================================
+// K1 generation 3 — CTA PAIR kernel (cluster of 2): each CTA owns ONE 128-row query tile of a 256-row pair.
+//
+// Why (DESIGN.md §3 K1, round-2 measurements): with two query tiles per CTA the 512 TMEM columns are exactly
+// [S0 | S1 | O0 | O1]; P_t has to overlay S_t, which orders Q_t K(j+1)^T behind P_t(j) V(j) and makes each tile's
+// S -> softmax -> P V -> next S chain (2 mbarrier hops + ~1700 cycles of softmax + 768 cycles of MMA) the period: 2850-2960
+// cycles per KV iteration against 2048 of tensor work. With ONE tile per CTA the columns are [S_a | S_b | P_a | P_b | O]:
+// scores and probabilities are double buffered, the MMA warp issues Q K(j+2)^T while P(j) is still being computed, and two
+// softmax warpgroups take alternate KV blocks (even / odd), so neither the tensor pipe nor the softmax warps wait for
+// each other in steady state. One tile per CTA would double the K/V fill per FLOP (L2 -> SM traffic above what the L2
+// delivers), so the two CTAs of a cluster load HALF of every K/V tile each and TMA-multicast it into both CTAs' shared
+// memory: the K/V traffic per 256 query rows is what it was.
+//
+//   warp 0      TMA producer   : own Q tile; keys [64c, 64c+64) of every K / V tile (c = CTA rank), multicast to both CTAs
+//   warp 1      MMA issuer     : step s: S_[s&1] = Q K(s)^T, then O += P_[s&1](s-2) V(s-2)   (tcgen05 cta_group::1)
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax of the even KV blocks, warps 8-11 of the odd ones (one thread per query row each)
+// The two warpgroups share the row state through the reference maximum: block j's group reads the reference block j-1
+// left in shared memory (`ref_bar`), rescales its own partial row sum if it moved, decides (lazily, threshold 2^8)
+// whether to raise it — rescaling O after P(j-1) V(j-1) retired — and publishes the result for block j+1. The row sum is
+// the sum of the two groups' partial sums once both are relative to the final reference.
+// K/V ring order (producer and consumer walk the same list): step s holds K(s) then V(s-2).
+// =====================================================================================================================
+template <int D>
+struct Cfg2 {
+  static constexpr int TILE_BYTES = 128 * D * 2;            // one Q / K / V tile
+  static constexpr int BOXES = D / 64;                      // 64-column (128-byte) TMA boxes per tile
+  static constexpr int KV_STAGES = (D == 128) ? 5 : 8;
+  static constexpr int SMEM_Q_OFF = 0;
+  static constexpr int SMEM_KV_OFF = TILE_BYTES;
+  static constexpr int SMEM_BAR_OFF = SMEM_KV_OFF + KV_STAGES * TILE_BYTES;
+  static constexpr int SMEM_XCH_OFF = SMEM_BAR_OFF + 512;   // mref[128], lsum[2][128] (fp32)
+  static constexpr int SMEM_BYTES = SMEM_XCH_OFF + 3 * 128 * 4 + 1024;
+  static constexpr uint32_t TMEM_S = 0;    // + buf * 128
+  static constexpr uint32_t TMEM_P = 256;  // + buf * 64
+  static constexpr uint32_t TMEM_O = 384;  // D columns
+};
+
+template <int D, typename T, bool ACCUM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+fa_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const Params p) {
+  using C = Cfg2<D>;
+  constexpr int NS = C::KV_STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + C::SMEM_BAR_OFF);  // [1]  TMA -> MMA
+  uint64_t* kv_full = q_full + 1;                                          // [NS] TMA (both CTAs' halves) -> MMA
+  uint64_t* kv_empty = kv_full + NS;                                       // [NS] MMA warps of BOTH CTAs -> TMA
+  uint64_t* s_full = kv_empty + NS;                                        // [2]  MMA -> softmax group buf
+  uint64_t* s_free = s_full + 2;                                           // [2]  softmax -> MMA: scores are in registers (4 warps)
+  uint64_t* p_half = s_free + 2;                                           // [half][group] softmax -> MMA: half of P stored (4 warps)
+  uint64_t* pv_done = p_half + 4;                                          // [2]  MMA -> softmax: P_buf consumed, O updated
+  uint64_t* ref_bar = pv_done + 2;                                         // [2]  softmax group -> the other group: reference published (4 warps)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(ref_bar + 2);
+  float* mref = reinterpret_cast<float*>(smem + C::SMEM_XCH_OFF);          // [128] reference max after the latest block
+  float* lsum = mref + 128;                                                // [2][128] partial row sums at the end
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();  // which 128-row tile of the pair, and which half of every K/V tile we load
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_half[2 * i], 4);
+      mbar_init(&p_half[2 * i + 1], 4);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&ref_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before any multicast load or commit can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // ---- work item: cluster = one 256-row pair of one (batch, head); heavy pairs first under a causal mask ----
+  const int pair_idx = p.causal ? (p.num_pairs - 1 - static_cast<int>(blockIdx.x >> 1)) : static_cast<int>(blockIdx.x >> 1);
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int kv_head = head / (p.Hq / p.Hkv);
+  int kv_len = p.Sk;
+  if (p.kv_lens != nullptr) kv_len = max(0, min(p.Sk, p.kv_lens[batch]));
+  const int coff = p.causal_bottom ? kv_len - p.Sq : static_cast<int>(p.causal_offset);
+  const int pair_row0 = pair_idx * 2 * BLOCK_M;
+  const int n_t0 = num_kv_tiles(p, pair_row0, kv_len, coff), n_t1 = num_kv_tiles(p, pair_row0 + BLOCK_M, kv_len, coff);
+  const int n_mine = __shfl_sync(0xffffffffu, cta == 0 ? n_t0 : n_t1, 0);
+  const int n_max = __shfl_sync(0xffffffffu, max(n_t0, n_t1), 0);   // the ring carries the K/V tiles either CTA needs
+  const int tile_row0 = pair_row0 + static_cast<int>(cta) * BLOCK_M;
+
+  if (warp_idx < 4) {
+    setmaxnreg_dec<72>();
+  }
+  if (warp_idx == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      if (n_mine > 0) {
+        mbar_arrive_expect_tx(q_full, C::TILE_BYTES);
+        uint8_t* sq = smem + C::SMEM_Q_OFF;
+#pragma unroll
+        for (int c = 0; c < C::BOXES; ++c) tma_load_4d(sq + c * 16384, &tmap_q, q_full, c * 64, head, tile_row0, batch);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_half = [&](const CUtensorMap* tm, int j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);  // both CTAs have released this stage
+        mbar_arrive_expect_tx(&kv_full[stage], C::TILE_BYTES);  // (our half + the peer's half land here)
+        uint8_t* dst = smem + C::SMEM_KV_OFF + stage * C::TILE_BYTES + cta * (64 * 128);  // rows [64c, 64c+64) of every box
+#pragma unroll
+        for (int c = 0; c < C::BOXES; ++c)
+          tma_load_4d_mcast(dst + c * 16384, tm, &kv_full[stage], c * 64, kv_head, j * BLOCK_N + static_cast<int>(cta) * 64, batch, 3);
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      };
+      for (int s = 0; s < n_max + 2; ++s) {
+        if (s < n_max) load_half(&tmap_k, s);
+        if (s >= 2) load_half(&tmap_v, s - 2);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ============================== MMA issuer ==============================
+    constexpr uint32_t idesc_qk = make_idesc_f16(BLOCK_M, BLOCK_N, Pack2<T>::kIsBf16, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_f16(BLOCK_M, D, Pack2<T>::kIsBf16, false, true);
+    const uint32_t sq_addr = smem_u32(smem + C::SMEM_Q_OFF);
+    const uint32_t skv_addr = smem_u32(smem + C::SMEM_KV_OFF);
+    const uint64_t qdesc0 = make_smem_desc_sw128(sq_addr, 16, 1024);
+    const uint64_t kdesc0 = make_smem_desc_sw128(skv_addr, 16, 1024);
+    const uint64_t vdesc0 = make_smem_desc_sw128(skv_addr, 16384, 1024);
+    constexpr uint32_t TILE16 = C::TILE_BYTES >> 4;
+    auto issue_qk = [&](int buf, int k_stage) {
+      const uint64_t kd = kdesc0 + static_cast<uint64_t>(k_stage * TILE16);
+      const uint32_t d_tmem = tmem_base + C::TMEM_S + static_cast<uint32_t>(buf * 128);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (ks >> 2) * 1024 + (ks & 3) * 2;  // 16-byte units: next 64-col box / next 32 bytes
+          umma_ss(d_tmem, qdesc0 + off, kd + off, idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[buf]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int buf, int v_stage, int part, bool accumulate) {
+      const uint64_t vd = vdesc0 + static_cast<uint64_t>(v_stage * TILE16);
+      const uint32_t d_tmem = tmem_base + C::TMEM_O;
+      const uint32_t p_tmem = tmem_base + C::TMEM_P + static_cast<uint32_t>(buf * 64);
+      if (elect_one()) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const int ks = part * 4 + k4;
+          umma_ts(d_tmem, p_tmem + ks * 8, vd + static_cast<uint64_t>(ks * 128), idesc_pv, (accumulate || ks > 0) ? 1u : 0u);
+        }
+        if (part == 1) umma_commit(&pv_done[buf]);
+      }
+      __syncwarp();
+    };
+    // the stage is free for the NEXT multicast load once the MMA warps of both CTAs have released it
+    auto release = [&](int stage) {
+      if (elect_one()) umma_commit_mcast(&kv_empty[stage], 3);
+      __syncwarp();
+    };
+    if (n_mine > 0) mbar_wait(q_full, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    auto advance = [&]() { if (++stage == NS) { stage = 0; phase ^= 1; } };
+    for (int s = 0; s < n_max + 2; ++s) {
+      if (s < n_max) {  // K(s)
+        mbar_wait(&kv_full[stage], phase);
+        if (s < n_mine) {
+          const int buf = s & 1;
+          if (s >= 2) mbar_wait(&s_free[buf], static_cast<uint32_t>(((s - 2) >> 1) & 1));  // S(s-2) is in registers
+          tc_fence_after();
+          issue_qk(buf, stage);
+        }
+        release(stage);
+        advance();
+      }
+      if (s >= 2) {     // V(s-2)
+        const int j = s - 2;
+        mbar_wait(&kv_full[stage], phase);
+        if (j < n_mine) {
+          const int buf = j & 1;
+          const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
+          mbar_wait(&p_half[buf], par);        // (p_half[half][group])
+          tc_fence_after();
+          issue_pv(buf, stage, 0, j > 0);
+          mbar_wait(&p_half[2 + buf], par);
+          tc_fence_after();
+          issue_pv(buf, stage, 1, true);
+        }
+        release(stage);
+        advance();
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ============================== softmax / correction / epilogue ==============================
+    setmaxnreg_inc<216>();
+    const int w = (warp_idx - 4) >> 2;           // 0: even KV blocks, 1: odd KV blocks
+    const int quad = warp_idx & 3;               // TMEM lane quadrant
+    const int row = quad * 32 + lane;            // row inside the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + C::TMEM_S + static_cast<uint32_t>(w * 128);
+    const uint32_t tP = tmem_base + lane_addr + C::TMEM_P + static_cast<uint32_t>(w * 64);
+    const uint32_t tO = tmem_base + lane_addr + C::TMEM_O;
+    // barrier addresses as two opaque base registers (this group's / the other group's slot) + constant offsets
+    // (see smem_addr_opaque); p_half is laid out [half][group] so that it follows the same rule
+    const uint32_t base_w = smem_addr_opaque(q_full) + static_cast<uint32_t>(w) * 8u;
+    const uint32_t base_o = base_w + 8u - static_cast<uint32_t>(w) * 16u;   // (w ^ 1) * 8
+    auto bar_off = [&](const uint64_t* b0) { return static_cast<uint32_t>((b0 - q_full) * 8); };
+    const uint32_t a_s_full = base_w + bar_off(s_full);
+    const uint32_t a_s_free = base_w + bar_off(s_free);
+    const uint32_t a_p_half = base_w + bar_off(p_half);   // + half * 16
+    const uint32_t a_pv_mine = base_w + bar_off(pv_done);
+    const uint32_t a_pv_other = base_o + bar_off(pv_done);
+    const uint32_t a_ref_mine = base_w + bar_off(ref_bar);
+    const uint32_t a_ref_other = base_o + bar_off(ref_bar);
+
+    const int q_row = tile_row0 + row;
+    float m_own = -INFINITY;  // reference max (log2 units) this group's l_run (and the P it stored last) are relative to
+    float l_run = 0.f;        // this group's share of the row sum
+    const int64_t q_pos_plus = static_cast<int64_t>(q_row) + coff;  // last visible key under causal
+    // exp2(a - b) with the convention exp2(-inf - x) = 0, also for x = -inf
+    auto ratio = [](float a, float b) { return a == -INFINITY ? 0.f : fast_exp2(a - b); };
+
+    for (int j = w; j < n_mine; j += 2) {
+      const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
+      mbar_wait_addr(a_s_full, par);
+      tc_fence_after();
+      uint32_t s[128];
+      tmem_ld_x32(tS + 0, s + 0);
+      tmem_ld_x32(tS + 32, s + 32);
+      tmem_ld_x32(tS + 64, s + 64);
+      tmem_ld_x32(tS + 96, s + 96);
+      tmem_wait_ld();
+      // the scores are in registers: the buffer goes back to the MMA warp for Q K(j+2)^T
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(a_s_free);
+      // ---- masking: keys >= limit (relative to the tile) are invisible ----
+      const int kv0 = j * BLOCK_N;
+      int limit = kv_len - kv0;
+      if (p.causal) {
+        const int64_t cl = q_pos_plus - kv0 + 1;
+        if (cl < limit) limit = static_cast<int>(cl < 0 ? 0 : cl);
+      }
+      if (limit < BLOCK_N) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= limit) s[c] = 0xFF800000u;  // -inf
+      }
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      float2 nm2, sum2;
+      uint32_t pk0[32], pk1[32];
+#ifndef B200_FA_PAIR_POLY_MOD
+#define B200_FA_PAIR_POLY_MOD 4
+#endif
+      auto exp_pair = [&](int c) -> uint32_t {
+        const float2 x = __ffma2_rn(make_float2(__uint_as_float(s[c]), __uint_as_float(s[c + 1])), sc2, nm2);
+        const bool poly = B200_FA_PAIR_POLY_MOD > 0 && ((c >> 1) % (B200_FA_PAIR_POLY_MOD > 0 ? B200_FA_PAIR_POLY_MOD : 1)) == 1;
+        const float2 e = poly ? exp2_poly2(x) : make_float2(fast_exp2(x.x), fast_exp2(x.y));
+        sum2 = __fadd2_rn(sum2, e);
+        return Pack2<T>::pack(e.x, e.y);
+      };
+      auto set_reference = [&](float m) {
+        const float m_ref = (m == -INFINITY) ? 0.f : m;
+        nm2 = make_float2(-m_ref, -m_ref);
+        sum2 = make_float2(0.f, 0.f);
+      };
+      auto publish = [&](int half) {
+        tmem_wait_st();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(a_p_half + static_cast<uint32_t>(half) * 16u);
+      };
+      // ---- speculative first half against the reference this group used last (it rarely moves, see K1 notes) ----
+      const float m_spec = m_own;
+      set_reference(m_spec);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+      // ---- row max of this block ----
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[c + 0]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      // ---- the reference block j-1 (other group) left behind ----
+      float m_in = -INFINITY;
+      if (j >= 1) {
+        mbar_wait_addr(a_ref_other, static_cast<uint32_t>(((j - 1) >> 1) & 1));
+        m_in = mref[row];
+      }
+      if (m_in != m_own) l_run *= ratio(m_own, m_in);  // our partial sum follows the reference the other group moved
+      // ---- lazy rescale decision for block j ----
+      float m_out = m_in, alpha = 1.0f;
+      bool rescale = false;
+      if (m_tile > m_in + kRescaleThreshold) {  // (m_in = -inf until the first visible key)
+        m_out = m_tile;
+        alpha = ratio(m_in, m_out);
+        l_run *= alpha;
+        rescale = true;
+      }
+      if (__any_sync(0xffffffffu, rescale) && j > 0) {
+        // O must contain P(j-1) V(j-1) (other group's buffer) before it is rescaled
+        mbar_wait_addr(a_pv_other, static_cast<uint32_t>(((j - 1) >> 1) & 1));
+        tc_fence_after();
+        // (rare path, rolled loop of 16-column pieces: a 32-register block here makes ptxas route the S registers of
+        // the hot path through local memory)
+#pragma unroll 1
+        for (int c = 0; c < D / 16; ++c) {
+          uint32_t o[16];
+          tmem_ld_x16(tO + c * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_x16(tO + c * 16, o);
+        }
+        tmem_wait_st();
+      }
+      // ---- publish the reference (and the rescaled O) for block j+1 ----
+      mref[row] = m_out;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(a_ref_mine);
+      m_own = m_out;
+      if (__any_sync(0xffffffffu, m_out != m_spec)) {
+        // the speculation failed for at least one row of this warp: redo the first half against the reference in force
+        set_reference(m_out);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) pk0[i] = exp_pair(2 * i);
+      }
+      // ---- our P buffer is free once P(j-2) V(j-2) retired ----
+      if (j >= 2) {
+        mbar_wait_addr(a_pv_mine, static_cast<uint32_t>(((j - 2) >> 1) & 1));
+        tc_fence_after();
+      }
+      tmem_st_x32(tP, pk0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk1[i] = exp_pair(64 + 2 * i);
+      publish(0);
+#pragma unroll
+      for (int i = 16; i < 32; ++i) pk1[i] = exp_pair(64 + 2 * i);
+      tmem_st_x32(tP + 32, pk1);
+      l_run += sum2.x + sum2.y;
+      publish(1);
+    }
+
+    // ---- epilogue: both groups agree on the final reference, add their partial sums, and write half of the columns each ----
+    if (tile_row0 < p.Sq) {
+      const bool row_ok = q_row < p.Sq;
+      float m_fin = m_own;
+      if (n_mine > 0) {
+        const int wl = (n_mine - 1) & 1;  // the group that processed the last block holds the final reference
+        if (w != wl) {
+          mbar_wait_addr(a_ref_other, static_cast<uint32_t>(((n_mine - 1) >> 1) & 1));
+          m_fin = mref[row];
+          if (m_fin != m_own) l_run *= ratio(m_own, m_fin);
+        }
+      }
+      [[maybe_unused]] float lse_old = -INFINITY;
+      if constexpr (ACCUM) {
+        if (!p.acc_init && row_ok)
+          lse_old = p.lse_acc[static_cast<int64_t>(batch) * p.lse_sb + static_cast<int64_t>(head) * p.lse_sh + q_row];
+      }
+      lsum[w * 128 + row] = l_run;
+      named_bar_sync(1, 256);
+      const float l_tot = lsum[row] + lsum[128 + row];
+      float inv_l = 0.f;
+      float lse_val = -INFINITY;
+      if (n_mine > 0) {
+        const int wl = (n_mine - 1) & 1;
+        mbar_wait_addr(wl == w ? a_pv_mine : a_pv_other, static_cast<uint32_t>(((n_mine - 1) >> 1) & 1));
+        tc_fence_after();
+        if (l_tot > 0.f && m_fin != -INFINITY) {  // (a row without a visible key keeps the reference at -inf)
+          inv_l = 1.0f / l_tot;
+          lse_val = (m_fin + log2f(l_tot)) * kLn2;
+        }
+      }
+      const uint32_t tOh = tO + static_cast<uint32_t>(w * (D / 2));
+      if constexpr (!ACCUM) {
+        if (p.lse != nullptr && row_ok && w == 0) p.lse[(static_cast<int64_t>(batch) * p.Hq + head) * p.Sq + q_row] = lse_val;
+        T* orow = reinterpret_cast<T*>(p.o) + static_cast<int64_t>(batch) * p.o_sb + static_cast<int64_t>(q_row) * p.o_ss +
+                  static_cast<int64_t>(head) * p.o_sh + w * (D / 2);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+          uint32_t o[32];
+          if (n_mine > 0) {
+            tmem_ld_x32(tOh + c * 32, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint4 pk;
+              pk.x = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 0]) * inv_l, __uint_as_float(o[q4 * 8 + 1]) * inv_l);
+              pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
+              pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
+              pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
+            }
+          }
+        }
+      } else {
+        float* lrow = p.lse_acc + static_cast<int64_t>(batch) * p.lse_sb + static_cast<int64_t>(head) * p.lse_sh + q_row;
+        float* arow = p.o_acc + static_cast<int64_t>(batch) * p.acc_sb + static_cast<int64_t>(q_row) * p.acc_ss +
+                      static_cast<int64_t>(head) * p.acc_sh + w * (D / 2);
+        float w_old = 0.f, w_new = inv_l, lse_out = lse_val;
+        if (!p.acc_init && row_ok) {
+          const float mx = fmaxf(lse_old, lse_val);
+          if (mx == -INFINITY) {
+            w_old = 0.f;
+            w_new = 0.f;
+            lse_out = -INFINITY;
+          } else {
+            const float e_old = fast_exp2((lse_old - mx) * kLog2e);
+            const float e_new = fast_exp2((lse_val - mx) * kLog2e);
+            const float den = e_old + e_new;
+            lse_out = mx + log2f(den) * kLn2;
+            w_old = e_old / den;
+            w_new = e_new / den * inv_l;
+          }
+        }
+        const bool touch = row_ok && (p.acc_init || lse_val != -INFINITY);
+        if (touch && w == 0) *lrow = lse_out;
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+          uint32_t o[32];
+          if (n_mine > 0) {
+            tmem_ld_x32(tOh + c * 32, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = 0u;
+          }
+          if (touch) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              float4* dst = reinterpret_cast<float4*>(arow + c * 32 + q4 * 4);
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!p.acc_init) a = *dst;
+              a.x = a.x * w_old + __uint_as_float(o[q4 * 4 + 0]) * w_new;
+              a.y = a.y * w_old + __uint_as_float(o[q4 * 4 + 1]) * w_new;
+              a.z = a.z * w_old + __uint_as_float(o[q4 * 4 + 2]) * w_new;
+              a.w = a.w * w_old + __uint_as_float(o[q4 * 4 + 3]) * w_new;
+              *dst = a;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still multicast into / arrive on this CTA's shared memory until it is done too
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D, typename T, bool ACCUM>
+int launch_pair(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const Params& p, cudaStream_t stream) {
+  auto kern = fa_fwd_pair_kernel<D, T, ACCUM>;
+  static bool attr_set[64] = {};  // per device
+  B200_CUDA_OK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), Cfg2<D>::SMEM_BYTES, attr_set));
+  dim3 grid(2 * p.num_pairs, p.Hq, p.B);  // clusters of 2 along x: the two 128-row tiles of a pair
+  kern<<<grid, NUM_THREADS, Cfg2<D>::SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  B200_CUDA_OK(cudaGetLastError());
+  note_launch("fa_fwd_pair_kernel");
+  return B200_OK;
+}
+
 static int make_bshd_tmap(CUtensorMap* out, const void* base, int B, int S, int H, int D, const int64_t strides[3],
-                          const char* name) {
+                          const char* name, uint32_t box_rows = 128) {
   // tensor addressed as [b][s][h][d] with element strides (b, s, h); TMA dims innermost-first: (d, h, s, b)
   for (int i = 0; i < 3; ++i)
     if (strides[i] <= 0 || strides[i] % 8 != 0)
@@ -675,7 +1171,7 @@ static int make_bshd_tmap(CUtensorMap* out, const void* base, int B, int S, int 
                       static_cast<uint64_t>(B)};
   uint64_t str[3] = {static_cast<uint64_t>(strides[2]) * 2, static_cast<uint64_t>(strides[1]) * 2,
                      static_cast<uint64_t>(strides[0]) * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t box[4] = {64, 1, box_rows, 1};
   return encode_tmap_sw128_16b(out, base, 4, dims, str, box);
 }
 
@@ -705,6 +1201,10 @@ static int run(const void* q, const void* k, const void* v, int B, int Sq, int S
   B200_CHECK_ARG(B <= 65535 && Hq <= 65535, "fa_fwd: B and Hq must be <= 65535");
   CUtensorMap tq, tk, tv;
   int rc;
+  // CTA-pair kernel (one 128-row tile per CTA, K/V multicast across the pair): B200_FA_PAIR=1/0 forces it on/off
+  // (read per call: tests flip it inside one process). It does not read the paged cache.
+  const char* pair_env = getenv("B200_FA_PAIR");
+  const bool use_pair = p.block_table == nullptr && (pair_env != nullptr ? pair_env[0] == '1' : kPairDefault);
   if ((rc = make_bshd_tmap(&tq, q, B, Sq, Hq, D, q_strides, "q"))) return rc;
   if (p.block_table != nullptr) {
     // paged: k / v point at the layer's slice of the cache; k_strides = (block, token, head) element strides, box = one block
@@ -719,8 +1219,8 @@ static int run(const void* q, const void* k, const void* v, int B, int Sq, int S
     }
     Sk = p.max_blocks * p.block_size;  // the key range the kernel walks is bounded by the block table
   } else {
-    if ((rc = make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k"))) return rc;
-    if ((rc = make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v"))) return rc;
+    if ((rc = make_bshd_tmap(&tk, k, B, Sk, Hkv, D, k_strides, "k", use_pair ? 64 : 128))) return rc;
+    if ((rc = make_bshd_tmap(&tv, v, B, Sk, Hkv, D, v_strides, "v", use_pair ? 64 : 128))) return rc;
   }
   // B200_FA_PERSISTENT=0 in the environment: every CTA handles only its own block (no work stealing)
   static const bool persistent = [] { const char* e = getenv("B200_FA_PERSISTENT"); return !(e && e[0] == '0'); }();
@@ -733,6 +1233,14 @@ static int run(const void* q, const void* k, const void* v, int B, int Sq, int S
   p.num_pairs = (Sq + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool bf = dtype == B200_DTYPE_BF16;
+  if (use_pair) {
+    if (accum) {
+      if (D == 128) return bf ? launch_pair<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch_pair<128, __half, true>(tq, tk, tv, p, s);
+      return bf ? launch_pair<64, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch_pair<64, __half, true>(tq, tk, tv, p, s);
+    }
+    if (D == 128) return bf ? launch_pair<128, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch_pair<128, __half, false>(tq, tk, tv, p, s);
+    return bf ? launch_pair<64, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch_pair<64, __half, false>(tq, tk, tv, p, s);
+  }
   if (accum) {
     if (D == 128) return bf ? launch<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<128, __half, true>(tq, tk, tv, p, s);
     return bf ? launch<64, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<64, __half, true>(tq, tk, tv, p, s);

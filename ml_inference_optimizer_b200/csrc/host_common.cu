@@ -73,6 +73,7 @@ std::atomic<int> g_sm_limit{0};
 std::atomic<int> g_group_rows{0};  // 0 = choose from the L2 budget
 std::atomic<long long> g_launches{0};
 std::atomic<const char*> g_last_gemm{""};
+std::atomic<const char*> g_last_kernel{""};
 
 cudaError_t set_max_dynamic_smem(const void* func, int bytes, bool (&slot)[64]) {
   int dev = 0;
@@ -86,6 +87,7 @@ cudaError_t set_max_dynamic_smem(const void* func, int bytes, bool (&slot)[64]) 
 
 void note_launch(const char* kernel_name, bool is_gemm) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_last_kernel.store(kernel_name, std::memory_order_relaxed);
   if (is_gemm) g_last_gemm.store(kernel_name, std::memory_order_relaxed);
 }
 
@@ -128,6 +130,8 @@ int b200_set_gemm_group_rows(int rows) {
 int64_t b200_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
 
 const char* b200_last_gemm_kernel(void) { return b200::g_last_gemm.load(std::memory_order_relaxed); }
+
+const char* b200_last_kernel(void) { return b200::g_last_kernel.load(std::memory_order_relaxed); }
 
 int b200_arch_ok(void) {
   int dev = 0;

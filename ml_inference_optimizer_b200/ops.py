@@ -493,6 +493,11 @@ def launch_count() -> int:
     return int(_lib.load().b200_launch_count())
 
 
+def last_kernel() -> str:
+    """Name of the kernel the library launched last (``b200_last_kernel``)."""
+    return (_lib.load().b200_last_kernel() or b"").decode()
+
+
 def last_gemm_kernel() -> str:
     """Name of the GEMM kernel the last linear / FusedMLP call dispatched to."""
     return (_lib.load().b200_last_gemm_kernel() or b"").decode()

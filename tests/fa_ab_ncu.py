@@ -22,7 +22,9 @@ def run(lib, q, k, v, o, causal):
                          st(v), st(o), D ** -0.5, int(causal), 0, None, 0, torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.b200_last_error()
 
-names = sys.argv[1:2] or ["new"]  # one build per process: template-static state is shared between copies of the library
+names = sys.argv[1:2] or ["new"]
+if names[0].startswith("pair"):
+    os.environ["B200_FA_PAIR"] = "1"  # the CTA-pair kernel of the same library (read per call)  # one build per process: template-static state is shared between copies of the library
 libs = {}
 for n in names:
     src = n.split(":")[0]

@@ -83,6 +83,56 @@ def test_fa_fwd_vs_oracle(ops, B, Sq, Sk, Hq, Hkv, D, causal, offset, kv_lens):
     check_lse(lse, rl)
 
 
+PAIR_CASES = FA_CASES + [
+    (2, 640, 640, 4, 2, 128, True, 0, None),         # odd number of 128-row tiles: the second CTA of the last cluster has no rows
+    (1, 1536, 1536, 2, 2, 64, True, 0, [1000]),      # padding + causal, D = 64
+    (1, 384, 2048, 2, 1, 128, False, 0, [1500]),     # 12-16 KV blocks per tile: both softmax groups take several blocks
+    (3, 768, 768, 6, 6, 128, True, 0, None),
+]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,Hq,Hkv,D,causal,offset,kv_lens", PAIR_CASES)
+def test_fa_pair_kernel_vs_oracle(ops, monkeypatch, B, Sq, Sk, Hq, Hkv, D, causal, offset, kv_lens):
+    """The CTA-pair kernel (one 128-row tile per CTA, S and P double-buffered in TMEM, two softmax warpgroups on alternate KV
+    blocks sharing the running reference maximum, K/V halves TMA-multicast across the cluster) is opt-in
+    (B200_FA_PAIR=1, read per call); it must agree with the oracle on every case of the default kernel, including tiles
+    whose two CTAs need different numbers of KV blocks and rows without a visible key."""
+    monkeypatch.setenv("B200_FA_PAIR", "1")
+    q, k, v = rand_qkv(B, Sq, Sk, Hq, Hkv, D)
+    lens = None if kv_lens is None else torch.tensor(kv_lens, device="cuda", dtype=torch.int32)
+    o, lse = ops.flash_attn_fwd(q, k, v, causal=causal, causal_offset=offset, kv_lens=lens, return_lse=True)
+    assert ops.last_kernel() == "fa_fwd_pair_kernel"
+    ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=causal, causal_offset=offset,
+                               kv_lens=None if lens is None else lens.cpu())
+    check_out(o, ro)
+    check_lse(lse, rl)
+    o2, lse2 = ops.flash_attn_fwd(q, k, v, causal=causal, causal_offset=offset, kv_lens=lens, return_lse=True)
+    assert torch.equal(o, o2) and torch.equal(lse, lse2)   # run-to-run bit equality (no atomics, fixed reduction order)
+
+
+def test_fa_pair_kernel_large_scores_and_accumulate(ops, monkeypatch):
+    """Lazy rescaling across the two softmax groups (the reference maximum moves by far more than 2^8 between blocks that
+    different warpgroups own) and the accumulate (ring-step) epilogue of the pair kernel."""
+    monkeypatch.setenv("B200_FA_PAIR", "1")
+    B, S, H, D = 1, 1024, 2, 128
+    q, k, v = rand_qkv(B, S, S, H, H, D, seed=5)
+    k = k.clone()
+    for blk, gain in ((1, 6.0), (2, 0.1), (3, 12.0), (6, 25.0)):   # block maxima jump up and down between the groups
+        k[:, blk * 128:(blk + 1) * 128] *= gain
+    o, lse = ops.flash_attn_fwd(q, k, v, causal=False, return_lse=True)
+    ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=False)
+    check_out(o, ro)
+    check_lse(lse, rl)
+    o_acc = torch.full((B, S, H, D), float("nan"), device="cuda", dtype=torch.float32)
+    lse_acc = torch.full((B, H, S), float("nan"), device="cuda", dtype=torch.float32)
+    for i, (a, b) in enumerate(((0, 384), (384, 512), (512, 1024))):
+        ops.flash_attn_fwd_accum(q, k[:, a:b], v[:, a:b], o_acc, lse_acc, init=(i == 0), causal=True, causal_offset=-a)
+        assert ops.last_kernel() == "fa_fwd_pair_kernel"
+    ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=True)
+    check_out(ops.cast_out(o_acc, q.dtype), ro)
+    check_lse(lse_acc, rl)
+
+
 @pytest.mark.parametrize("B,S,H,Hkv,D,causal,kv_lens", [
     (6, 256, 64, 64, 64, True, None),                     # 384 one/two-iteration items: > 2 per SM, every CTA steals blocks
     (3, 768, 80, 16, 128, True, None),                    # 720 items, GQA 5:1, mixed item lengths (heavy-first order)
