@@ -279,11 +279,37 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a
 }
 
 constexpr int GQA_WARPS = 4;
+constexpr bool kGqaRingDefault = false;
 // resident CTAs per SM the register allocation is capped for: two tiles of K/V are staged in registers per lane
 // (D = 128: 128 of ~250 registers -> 2 CTAs; D = 64: 64 of ~170 -> 3 CTAs, measured 4721 vs 4002 GB/s with 2)
 template <int D> struct GqaMinCtas { static constexpr int value = D == 128 ? 2 : 3; };
 
-template <int D, typename T, bool PAGED>
+// RING = true: every warp owns a ring of GQA_RING_STAGES K/V tiles in shared memory, filled by one 256-byte
+// cp.async.bulk per key row (lanes 0-15: K rows, lanes 16-31: V rows) that completes on the stage's mbarrier; the MMA
+// fragments are then read with conflict-free 128-bit shared loads (row pitches D*2+64 for K and D*2+16 for V). Two tiles
+// per warp are in flight while a third is being consumed (RING = false keeps one tile in flight in registers), and the
+// staging registers shrink from 128 to 64 per lane. The combine buffers of the epilogue alias the ring.
+constexpr int GQA_RING_STAGES = 3;
+template <int D> struct GqaRing {
+  static constexpr int KP = D * 2 + 64, VP = D * 2 + 16;          // row pitches in bytes
+  static constexpr int TILE_BYTES = 16 * KP + 16 * VP;
+  static constexpr int RING_BYTES = GQA_WARPS * GQA_RING_STAGES * TILE_BYTES;
+  static constexpr int BAR_OFF = RING_BYTES;
+  static constexpr int COMB_BYTES = (2 * GQA_WARPS * 16 + GQA_WARPS * 16 * D) * 4;
+  static constexpr int SMEM_BYTES = (RING_BYTES + GQA_WARPS * GQA_RING_STAGES * 8 > COMB_BYTES ? RING_BYTES + GQA_WARPS * GQA_RING_STAGES * 8 : COMB_BYTES);
+};
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar_smem) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(bar_smem)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+template <int D, typename T, bool PAGED, bool RING>
 __global__ void __launch_bounds__(GQA_WARPS * 32, GqaMinCtas<D>::value)
 decode_gqa_mma_kernel(const Params p, const int G) {
   constexpr int TILE = 16;       // keys per warp iteration
@@ -412,14 +438,70 @@ decode_gqa_mma_kernel(const Params p, const int G) {
     }
   };
   constexpr int STEP = GQA_WARPS * TILE;
-  uint4 krA[2][MB], vrA[DG][4], krB[2][MB], vrB[DG][4];
-  int t0 = k_begin + warp * TILE;
-  if (t0 < k_end) issue_tile(t0, krA, vrA);
-  for (; t0 < k_end; t0 += 2 * STEP) {
-    if (t0 + STEP < k_end) issue_tile(t0 + STEP, krB, vrB);
-    compute_tile(t0, krA, vrA);
-    if (t0 + 2 * STEP < k_end) issue_tile(t0 + 2 * STEP, krA, vrA);
-    if (t0 + STEP < k_end) compute_tile(t0 + STEP, krB, vrB);
+  extern __shared__ __align__(128) uint8_t gqa_dsm[];
+  if constexpr (RING) {
+    using R = GqaRing<D>;
+    constexpr int NSTG = GQA_RING_STAGES;
+    const uint32_t ring0 = smem_u32(gqa_dsm) + static_cast<uint32_t>(warp * NSTG * R::TILE_BYTES);
+    const uint32_t bar0 = smem_u32(gqa_dsm) + static_cast<uint32_t>(R::BAR_OFF + warp * NSTG * 8);
+    if (lane == 0) {
+#pragma unroll
+      for (int sidx = 0; sidx < NSTG; ++sidx) mbar_init(reinterpret_cast<uint64_t*>(gqa_dsm + R::BAR_OFF + (warp * NSTG + sidx) * 8), 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    const int first_t0 = k_begin + warp * TILE;
+    const int n_tiles = first_t0 < k_end ? (k_end - first_t0 + STEP - 1) / STEP : 0;
+    // tile i of this warp -> stage i % NSTG: lanes 0-15 copy the K rows, lanes 16-31 the V rows (256 bytes each at D = 128)
+    auto issue_ring = [&](const int i) {
+      const int t0 = first_t0 + i * STEP, stage = i % NSTG;
+      const int nvalid = min(TILE, k_end - t0);
+      const uint32_t bar = bar0 + static_cast<uint32_t>(stage * 8);
+      __syncwarp();  // every lane has finished reading the tile that lived in this stage
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(static_cast<uint32_t>(nvalid * 2 * D * 2)) : "memory");
+      }
+      __syncwarp();
+      const int r = lane & 15;
+      if (r < nvalid) {
+        const bool is_v = lane >= 16;
+        const T* src = (is_v ? vc : kc) + row_offset(t0 + r);
+        const uint32_t dst = ring0 + static_cast<uint32_t>(stage * R::TILE_BYTES + (is_v ? 16 * R::KP + r * R::VP : r * R::KP));
+        bulk_copy_g2s(dst, src, D * 2, bar);
+      }
+    };
+    for (int i = 0; i < NSTG - 1 && i < n_tiles; ++i) issue_ring(i);
+    for (int i = 0; i < n_tiles; ++i) {
+      if (i + NSTG - 1 < n_tiles) issue_ring(i + NSTG - 1);
+      const int t0 = first_t0 + i * STEP, stage = i % NSTG;
+      mbar_wait_addr(bar0 + static_cast<uint32_t>(stage * 8), static_cast<uint32_t>((i / NSTG) & 1));
+      const uint32_t kb = ring0 + static_cast<uint32_t>(stage * R::TILE_BYTES), vb = kb + 16 * R::KP;
+      uint4 kr[2][MB], vr[DG][4];
+#pragma unroll
+      for (int kg = 0; kg < 2; ++kg)
+#pragma unroll
+        for (int m = 0; m < MB; ++m) kr[kg][m] = lds128(kb + static_cast<uint32_t>((kg * 8 + g) * R::KP + (8 * t + 32 * m) * 2));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kr_ = 2 * t + (j & 1) + (j >> 1) * 8;
+        const bool valid = t0 + kr_ < k_end;  // rows past the end were not copied: they must read as zeros (0 x NaN)
+#pragma unroll
+        for (int d = 0; d < DG; ++d)
+          vr[d][j] = valid ? lds128(vb + static_cast<uint32_t>(kr_ * R::VP + (8 * g + 64 * d) * 2)) : make_uint4(0, 0, 0, 0);
+      }
+      compute_tile(t0, kr, vr);
+    }
+    __syncthreads();  // the combine buffers below alias the ring
+  } else {
+    uint4 krA[2][MB], vrA[DG][4], krB[2][MB], vrB[DG][4];
+    int t0 = k_begin + warp * TILE;
+    if (t0 < k_end) issue_tile(t0, krA, vrA);
+    for (; t0 < k_end; t0 += 2 * STEP) {
+      if (t0 + STEP < k_end) issue_tile(t0 + STEP, krB, vrB);
+      compute_tile(t0, krA, vrA);
+      if (t0 + 2 * STEP < k_end) issue_tile(t0 + 2 * STEP, krA, vrA);
+      if (t0 + STEP < k_end) compute_tile(t0 + STEP, krB, vrB);
+    }
   }
 
   // ---- combine: lanes of a row quad, then the warps of the CTA through shared memory ----
@@ -428,19 +510,26 @@ decode_gqa_mma_kernel(const Params p, const int G) {
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
   }
-  __shared__ float sm_m[GQA_WARPS][16];
-  __shared__ float sm_l[GQA_WARPS][16];
-  __shared__ float sm_acc[GQA_WARPS][16][D];
+  float* comb;
+  if constexpr (RING) {
+    comb = reinterpret_cast<float*>(gqa_dsm);
+  } else {
+    __shared__ float comb_static[2 * GQA_WARPS * 16 + GQA_WARPS * 16 * D];
+    comb = comb_static;
+  }
+  float* sm_m = comb;                          // [warp][16]
+  float* sm_l = comb + GQA_WARPS * 16;         // [warp][16]
+  float* sm_acc = comb + 2 * GQA_WARPS * 16;   // [warp][16][D]
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int row = g + 8 * r;
     if (row < G) {
-      if (t == 0) { sm_m[warp][row] = m_run[r]; sm_l[warp][row] = l_run[r]; }
+      if (t == 0) { sm_m[warp * 16 + row] = m_run[r]; sm_l[warp * 16 + row] = l_run[r]; }
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
         const int d = n >> 3, j = n & 7;
-        sm_acc[warp][row][64 * d + 8 * (2 * t) + j] = o[n][2 * r];
-        sm_acc[warp][row][64 * d + 8 * (2 * t + 1) + j] = o[n][2 * r + 1];
+        sm_acc[(warp * 16 + row) * D + 64 * d + 8 * (2 * t) + j] = o[n][2 * r];
+        sm_acc[(warp * 16 + row) * D + 64 * d + 8 * (2 * t + 1) + j] = o[n][2 * r + 1];
       }
     }
   }
@@ -449,14 +538,14 @@ decode_gqa_mma_kernel(const Params p, const int G) {
     const int row = idx / D, d = idx - row * D;
     float m = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < GQA_WARPS; ++w) m = fmaxf(m, sm_m[w][row]);
+    for (int w = 0; w < GQA_WARPS; ++w) m = fmaxf(m, sm_m[w * 16 + row]);
     const float m_safe = (m == -INFINITY) ? 0.f : m;
     float l = 0.f, acc = 0.f;
 #pragma unroll
     for (int w = 0; w < GQA_WARPS; ++w) {
-      const float c = fast_exp2(sm_m[w][row] - m_safe);
-      l = fmaf(sm_l[w][row], c, l);
-      acc = fmaf(sm_acc[w][row][d], c, acc);
+      const float c = fast_exp2(sm_m[w * 16 + row] - m_safe);
+      l = fmaf(sm_l[w * 16 + row], c, l);
+      acc = fmaf(sm_acc[(w * 16 + row) * D + d], c, acc);
     }
     const float out = l > 0.f ? acc / l : 0.f;
     const float lse = l > 0.f ? (m + log2f(l)) * kLn2 : -INFINITY;
@@ -613,10 +702,27 @@ int launch_decode(const Params& p, bool paged, cudaStream_t stream) {
 template <int D, typename T>
 int launch_decode_gqa(int G, const Params& p, bool paged, cudaStream_t stream) {
   dim3 grid(p.splits, p.Hkv, p.B);
-  if (paged) decode_gqa_mma_kernel<D, T, true><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
-  else decode_gqa_mma_kernel<D, T, false><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
-  B200_CUDA_OK(cudaGetLastError());
-  note_launch("decode_gqa_mma_kernel");
+  // B200_GQA_RING=0/1 selects the register-staged / shared-memory-ring variant (read per call)
+  const char* ring_env = getenv("B200_GQA_RING");
+  const bool ring = ring_env != nullptr ? ring_env[0] == '1' : kGqaRingDefault;
+  if (ring) {
+    constexpr int kSmem = GqaRing<D>::SMEM_BYTES;
+    static bool attr_p[64] = {}, attr_c[64] = {};
+    if (paged) {
+      B200_CUDA_OK(set_max_dynamic_smem(reinterpret_cast<const void*>(decode_gqa_mma_kernel<D, T, true, true>), kSmem, attr_p));
+      decode_gqa_mma_kernel<D, T, true, true><<<grid, GQA_WARPS * 32, kSmem, stream>>>(p, G);
+    } else {
+      B200_CUDA_OK(set_max_dynamic_smem(reinterpret_cast<const void*>(decode_gqa_mma_kernel<D, T, false, true>), kSmem, attr_c));
+      decode_gqa_mma_kernel<D, T, false, true><<<grid, GQA_WARPS * 32, kSmem, stream>>>(p, G);
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    note_launch("decode_gqa_ring_kernel");
+  } else {
+    if (paged) decode_gqa_mma_kernel<D, T, true, false><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
+    else decode_gqa_mma_kernel<D, T, false, false><<<grid, GQA_WARPS * 32, 0, stream>>>(p, G);
+    B200_CUDA_OK(cudaGetLastError());
+    note_launch("decode_gqa_mma_kernel");
+  }
   if (p.splits > 1) {
     decode_reduce_kernel<D, T><<<p.B * p.Hq, D, 0, stream>>>(p.part_o, p.part_lse, p.o, p.lse, p.splits);
     B200_CUDA_OK(cudaGetLastError());
