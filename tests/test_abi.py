@@ -76,3 +76,38 @@ def test_product_package_never_imports_the_oracle():
                 if f.endswith(".py"):
                     text = open(os.path.join(dirpath, f)).read()
                     assert not _re.search(r"^\s*(from|import)\s+oracle\b", text, _re.M), f"{top}/{f} imports the oracle"
+
+
+def test_build_is_keyed_on_source_content(built_lib, monkeypatch, tmp_path):
+    """The library on disk must have been built from exactly the current sources: the stamp next to it is a hash of the
+    sources, headers and flags; a stale or missing stamp (a prebuilt .so travelling with a snapshot, a checkout that reset
+    mtimes) forces a rebuild instead of being trusted."""
+    from ml_inference_optimizer_b200 import build as b
+
+    assert b.LIB_PATH.exists() and b.STAMP_PATH.exists()
+    assert b.STAMP_PATH.read_text().strip() == b.source_stamp()
+    assert not b.needs_build()
+    stale = tmp_path / "source_stamp.txt"
+    stale.write_text("0" * 64 + "\n")
+    monkeypatch.setattr(b, "STAMP_PATH", stale)
+    assert b.needs_build()
+    monkeypatch.setattr(b, "STAMP_PATH", tmp_path / "missing.txt")
+    assert b.needs_build()
+    monkeypatch.setenv("B200_EXTRA_NVCC_FLAGS", "-DSOMETHING_ELSE")   # other flags = another binary
+    assert b.source_stamp() != (b.PKG_DIR / "build" / "source_stamp.txt").read_text().strip()
+
+
+def test_lib_path_override_is_explicit(monkeypatch, tmp_path):
+    """B200_LIB_PATH (developer A/B runs) must name an existing file: a wrong path raises instead of silently loading the
+    default library."""
+    import importlib
+
+    from ml_inference_optimizer_b200 import _lib as L
+
+    monkeypatch.setenv("B200_LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(L, "_lib", None)
+    with pytest.raises(RuntimeError, match="missing"):
+        L.load()
+    monkeypatch.delenv("B200_LIB_PATH")
+    monkeypatch.setattr(L, "_lib", None)
+    assert L.load() is not None
