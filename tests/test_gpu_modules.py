@@ -365,3 +365,34 @@ def test_paged_generation_cuda_graph_matches_eager():
     assert torch.equal(graph, eager)
     assert c2.get_sequence_length(0) == c1.get_sequence_length(0) == 21 + 13
     assert len(c2.get_block_table(1)) == 3
+
+
+def test_triton_fused_attention_shim_vs_fp32_reference():
+    """``triton_fused_attention`` (QKV projection -> attention -> output projection, reference
+    kernels/triton/flash_attention_kernels.py:1361-1566 / :1719-1779) through K3 + K1 + K3 against the same composition in
+    fp32 with the oracle's attention; causal, with a right-padding mask, head_dim given explicitly."""
+    import torch.nn.functional as F
+
+    from kernels.triton.flash_attention_kernels import pytorch_fused_attention, triton_fused_attention
+    from oracle import attn_mlp_oracle as orc
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, S, H, D = 2, 320, 6, 64
+    hidden = H * D
+    r = lambda *s, sc=1.0: (torch.randn(*s, device="cuda", generator=g) * sc).to(torch.bfloat16)
+    x, wqkv, bqkv = r(B, S, hidden), r(3 * hidden, hidden, sc=0.05), r(3 * hidden, sc=0.1)
+    wo, bo = r(hidden, hidden, sc=0.05), r(hidden, sc=0.1)
+    mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+    mask[1, 200:] = False
+    y = triton_fused_attention(x, wqkv, bqkv, wo, bo, mask=mask, causal=True, num_heads=H, head_dim=D)
+    assert y.shape == (B, S, hidden) and pytorch_fused_attention is triton_fused_attention
+    f = lambda t: t.float().cpu()
+    qkv = F.linear(f(x), f(wqkv), f(bqkv)).to(torch.bfloat16).float().view(B, S, 3, H, D)   # the GEMM output is bf16
+    q, k, v = qkv.unbind(2)
+    o, _ = orc.attention_ref(q, k, v, causal=True, kv_lens=torch.tensor([S, 200]))
+    ref = F.linear(o.to(torch.bfloat16).float().reshape(B, S, hidden), f(wo), f(bo))
+    err = (y.float().cpu() - ref).abs()
+    valid = torch.ones(B, S, dtype=torch.bool)
+    assert err[valid].max().item() <= 2e-2 * max(1.0, ref.abs().max().item() / 4), err.max().item()
+    with pytest.raises(ValueError):
+        triton_fused_attention(x, wqkv[:-8], bqkv, wo, bo, num_heads=H)
