@@ -204,6 +204,18 @@ class RingExchange:
             return
         nxt, prv = self._global((self.rank + 1) % self.world), self._global((self.rank - 1) % self.world)
         cuda = send[0].is_cuda
+        if cuda and dist.get_backend(self.group) == "gloo":
+            # gloo has no device-to-device send/recv: stage the hop through host memory (transport only — used when
+            # several ranks share one GPU, e.g. the single-GPU run of tests/multi_gpu_check.py; NCCL ranks never come here)
+            host_send = [s.cpu() for s in send]
+            self._staged = [(r, torch.empty(r.shape, dtype=r.dtype)) for r in recv]
+            ops_ = []
+            for s, (_, r) in zip(host_send, self._staged):
+                ops_.append(dist.P2POp(dist.isend, s, nxt, group=self.group))
+                ops_.append(dist.P2POp(dist.irecv, r, prv, group=self.group))
+            self._works = dist.batch_isend_irecv(ops_)
+            self._keep = host_send
+            return
         if cuda and self.use_side_stream:
             if self.stream is None:
                 self.stream = torch.cuda.Stream(device=send[0].device, priority=-1)
@@ -233,6 +245,10 @@ class RingExchange:
         else:
             for w in self._works:
                 w.wait()
+        if getattr(self, "_staged", None):
+            for dst, host in self._staged:
+                dst.copy_(host)
+            self._staged, self._keep = None, None
         self._works = None
 
 

@@ -16,10 +16,19 @@ import torch.nn.functional as F
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # B200_MGC_SHARED_GPU=1: every rank runs its kernels on cuda:0 and the ranks talk over gloo (NCCL refuses two ranks
+    # on one device) — the same checks on a box with ONE GPU: ring schedule + K1 accumulate steps + TP sharding with the
+    # real kernels; only the transport differs (host-staged hops, gloo all-reduce).
+    shared = os.environ.get("B200_MGC_SHARED_GPU", "") == "1"
+    if shared:
+        local = 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
-    dist.init_process_group("nccl", device_id=dev, pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
+    if shared:
+        dist.init_process_group("gloo")
+    else:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+        dist.init_process_group("nccl", device_id=dev, pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
     from oracle import attn_mlp_oracle as orc
     from parallelism import communication as comm
     from parallelism import parallel_utils as pu
@@ -53,6 +62,8 @@ def main():
     c = lambda t: t.to(dev)
     for name, act, gate in (("gelu", F.gelu, (None, None)), ("swiglu", F.silu, (wg, bg))):
         m = TensorParallelMLP.from_dense(c(wu), c(bu), c(wd), c(bd), cfg, act, *(None if t is None else c(t) for t in gate))
+        if shared:
+            m.reduce_impl = "nccl"  # (= torch.distributed.all_reduce on the group's backend; no symmetric memory over gloo)
         y = m(c(x))
         ref, pabs = orc.tp_mlp_ref(x, wu, bu, wd, bd, "swiglu" if gate[0] is not None else "gelu", world, *gate,
                                    return_partial_abs_sum=True)
@@ -65,6 +76,8 @@ def main():
     # prefill-sized input: the chunked path that overlaps the all-reduce with the next chunk's GEMMs
     xl = r(8192 + 77, h)
     m = TensorParallelMLP.from_dense(c(wu), c(bu), c(wd), c(bd), cfg, F.silu, c(wg), c(bg))
+    if shared:
+        m.reduce_impl = "nccl"
     y = m(c(xl))
     ref, pabs = orc.tp_mlp_ref(xl, wu, bu, wd, bd, "swiglu", world, wg, bg, return_partial_abs_sum=True)
     e = (y.float().cpu() - ref).abs().max().item()
