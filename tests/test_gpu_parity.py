@@ -589,3 +589,63 @@ def test_layernorm_golden_and_shim(ops, golden_dir):
     y = triton_layernorm(cu(d["x"]), cu(d["w"]), cu(d["b"]), d["eps"], cu(d["r"]), d["alpha"])
     assert y.shape == d["y"].shape
     check_out(y, d["y"], max_abs=6e-2, mean_rel=1e-2)  # inputs rounded to bf16 (|y| up to 6)
+
+
+# ------------------------------------------------------------------------------------------ guard rows (own bounds checks)
+def _guarded(shape, dtype, rows_dim, guard=3, fill=-7.0):
+    """A tensor of `shape` that is a view into a larger buffer with `guard` sentinel slices before and after along rows_dim."""
+    big_shape = list(shape)
+    big_shape[rows_dim] += 2 * guard
+    big = torch.full(big_shape, fill, device="cuda", dtype=dtype)
+    idx = [slice(None)] * len(shape)
+    idx[rows_dim] = slice(guard, guard + shape[rows_dim])
+    return big, big[tuple(idx)], idx
+
+
+def _guards_untouched(big, idx, rows_dim, guard=3, fill=-7.0):
+    lo = [slice(None)] * big.dim(); hi = [slice(None)] * big.dim()
+    lo[rows_dim] = slice(0, guard); hi[rows_dim] = slice(big.shape[rows_dim] - guard, None)
+    return bool((big[tuple(lo)] == fill).all()) and bool((big[tuple(hi)] == fill).all())
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_kernels_write_only_their_rows(ops, monkeypatch, pair):
+    """Outputs are views into larger buffers with sentinel rows on both sides: ragged row counts (partial last tiles, more
+    rows than resident CTAs, persistent loops with a prefetched next row) must not write a byte outside their rows —
+    attention (both prefill kernels), GQA decode (both staging variants), LayerNorm (warp and CTA kernels), linear."""
+    monkeypatch.setenv("B200_FA_PAIR", pair)
+    monkeypatch.setenv("B200_GQA_RING", pair)
+    bf = torch.bfloat16
+    # prefill attention: the sequence dimension is guarded ([B, S, H, D] view with the same strides as the buffer)
+    q, k, v = rand_qkv(2, 333, 333, 4, 2, 128, seed=9)
+    big, out, idx = _guarded((2, 333, 4, 128), bf, rows_dim=1)
+    ops.flash_attn_fwd(q, k, v, causal=True, out=out)
+    ro, _ = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=True)
+    check_out(out, ro)
+    assert _guards_untouched(big, idx, 1)
+    # decode (GQA 4:1): the batch dimension is guarded
+    g = torch.Generator(device="cuda").manual_seed(4)
+    qd = torch.randn(3, 16, 128, device="cuda", dtype=bf, generator=g)
+    kc = torch.randn(3, 777, 4, 128, device="cuda", dtype=bf, generator=g); vc = torch.randn_like(kc)
+    lens = torch.tensor([777, 1, 300], device="cuda", dtype=torch.int32)
+    big, out, idx = _guarded((3, 16, 128), bf, rows_dim=0)
+    ops.decode_attention(qd, kc, vc, lens, out=out)
+    rd, _ = orc.decode_attention_ref(qd.cpu(), kc.cpu(), vc.cpu(), lens.cpu())
+    check_out(out, rd)
+    assert _guards_untouched(big, idx, 0)
+    # LayerNorm: warp-per-row (768), CTA-per-row with more rows than resident CTAs (4104 columns, ragged width)
+    for rows, cols in ((1237, 768), (2111, 4104), (999, 2048)):
+        x = torch.randn(rows, cols, device="cuda", dtype=bf); r_ = torch.randn_like(x)
+        w_ = torch.randn(cols, device="cuda", dtype=bf); b_ = torch.randn(cols, device="cuda", dtype=bf)
+        big, out, idx = _guarded((rows, cols), bf, rows_dim=0)
+        ops.layernorm(x, w_, b_, 1e-5, residual=r_, out=out)
+        ref = orc.layernorm_ref(x.cpu(), w_.cpu(), b_.cpu(), 1e-5, r_.cpu(), 1.0)
+        check_out(out, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=5e-3)
+        assert _guards_untouched(big, idx, 0)
+    # linear (ragged T: the last 128-row tile is partial; TMA store clips)
+    x = torch.randn(300, 512, device="cuda", dtype=bf); w_ = (torch.randn(1024, 512, device="cuda") * 0.05).to(bf)
+    big, out, idx = _guarded((300, 1024), bf, rows_dim=0)
+    ops.linear_act(x, w_, None, None, out=out)
+    ref = x.float().cpu() @ w_.float().cpu().t()
+    check_out(out, ref, max_abs=2e-2 * max(1.0, ref.abs().max().item() / 4), mean_rel=1e-2)
+    assert _guards_untouched(big, idx, 0)
