@@ -7,6 +7,15 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for rows, cols in ((32768, 768), (32768, 1024), (32768, 2048), (32768, 4096), (32768, 8192)):
     x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16); r = torch.randn_like(x)
     w = torch.randn(cols, device="cuda", dtype=torch.bfloat16); b = torch.randn_like(w)
+    # what a plain device copy of the same footprint reaches (the size-matched roofline: MEASURED_PEAKS' 6555 GB/s is a 4 GB copy)
+    yc = torch.empty_like(x); ts = []
+    for _ in range(12):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); yc.copy_(x); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"COPY rows={rows} cols={cols}: {ms*1e3:7.1f} us  {rows * cols * 4 / ms / 1e6:7.0f} GB/s (torch copy_ of the same tensor, read + write)", flush=True)
     variants = [(None, "1", "", ""), (r, "1", "", "")]
     if cols > 1024:
         variants += [(rr, "1", nm, pc) for rr in (None, r) for nm in (["512"] if cols <= 2048 else [""]) for pc in ("", "2", "3", "4")]
