@@ -144,7 +144,7 @@ int b200_cast_out(const float* o_acc, void* o, int B, int Sq, int Hq, int D, con
  *   workspace : device scratch of at least b200_fa_decode_workspace_bytes(...) bytes (may be NULL when the
  *               resolved num_splits == 1).                                                               */
 int64_t b200_fa_decode_workspace_bytes(int B, int Hq, int Hkv, int D, int max_context_len, int num_splits);
-int b200_fa_decode_num_splits(int B, int Hkv, int max_context_len);
+int b200_fa_decode_num_splits(int B, int Hq, int Hkv, int D, int max_context_len);
 int b200_fa_decode(const void* q, const void* k_cache, const void* v_cache, void* o, float* lse, int B, int Hq,
                    int Hkv, int D, const int32_t* context_lens, int max_context_len, float softmax_scale, int layout,
                    int64_t kv_batch_stride, int64_t kv_token_stride, const int32_t* block_table,

@@ -42,7 +42,7 @@ SIGNATURES = {
                                c_void_p]),
     "b200_cast_out": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int64_p, c_int, c_void_p]),
     "b200_fa_decode_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
-    "b200_fa_decode_num_splits": (c_int, [c_int, c_int, c_int]),
+    "b200_fa_decode_num_splits": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "b200_fa_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
                                c_int, c_float, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_int64, c_int, c_void_p]),

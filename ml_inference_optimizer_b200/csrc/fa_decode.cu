@@ -750,14 +750,39 @@ int dispatch_group(int G, const Params& p, bool paged, cudaStream_t stream) {
 
 extern "C" {
 
-int b200_fa_decode_num_splits(int B, int Hkv, int max_context_len) {
-  if (B <= 0 || Hkv <= 0 || max_context_len <= 0) return 1;
+int b200_fa_decode_num_splits(int B, int Hq, int Hkv, int D, int max_context_len) {
+  if (B <= 0 || Hq <= 0 || Hkv <= 0 || D <= 0 || max_context_len <= 0) return 1;
   const int sms = b200::sm_count();
-  const int64_t ctas = static_cast<int64_t>(B) * Hkv;
-  // 2-3 CTAs are resident per SM; aim for >= 4 waves so that the partial last wave costs little (a 1.15-wave launch
-  // left the GQA decode at 58% of the bandwidth it reaches with 4 splits)
-  const int64_t target = 12LL * sms;
-  int splits = static_cast<int>((target + ctas - 1) / ctas);
+  const int64_t ctas = static_cast<int64_t>(B) * Hkv;   // CTAs per split
+  const int G = Hq / Hkv;
+  // resident CTAs: 2 per SM for the MHA kernel and the D = 128 tensor-core GQA kernel, 3 for the D = 64 GQA kernel
+  const int64_t resident = static_cast<int64_t>(sms) * ((G >= 3 && G <= 16 && D == 64) ? 3 : 2);
+  // Measured (tests/decode_split_probe.py, profiles/r2_decode_splits.jsonl): a problem that fits in one wave is fastest
+  // with ONE nearly full wave and a power-of-two split count (even key ranges) — MQA B=32 8K: 8 splits 46 us vs the 32 of
+  // the old ">= 4 waves" rule 79 us; GQA B=8: 4 -> 64 us vs 28 -> 81 us (5 splits = 1.08 waves: 89 us); GQA B=1 32K: 32 ->
+  // 40 us vs 128 -> 56 us. If the largest such wave leaves more than a fifth of the slots empty and the problem is large
+  // enough to be bandwidth-bound (>= 256 MB of K/V), several waves win instead (D = 64 GQA B=64: 8 splits 108 us vs 1
+  // split 127 us). One to four waves: 1, 2 or 4 splits by how full the last wave is. Four waves and more: not split.
+  int splits = 1;
+  if (ctas < resident) {
+    int s1 = 1;
+    while (ctas * (s1 * 2) <= resident) s1 *= 2;
+    splits = s1;
+    const double fill = static_cast<double>(ctas * s1) / static_cast<double>(resident);
+    const double kv_bytes = 2.0 * static_cast<double>(ctas) * max_context_len * D * 2.0;
+    if (fill < 0.8 && kv_bytes >= 256.0e6) {
+      int s4 = s1;
+      while (ctas * s4 < 4 * resident) s4 *= 2;
+      splits = s4;
+    }
+  } else if (ctas < 4 * resident) {
+    double best_eff = 0.0;
+    for (int s = 1; s <= 4; s *= 2) {
+      const double waves = static_cast<double>(ctas * s) / static_cast<double>(resident);
+      const double eff = waves / static_cast<double>(static_cast<int64_t>(waves + 0.999999));
+      if (eff > best_eff * 1.02) { best_eff = eff; splits = s; }
+    }
+  }
   const int max_by_len = (max_context_len + 255) / 256;  // keep >= 256 keys per split
   if (splits > max_by_len) splits = max_by_len;
   if (splits < 1) splits = 1;
@@ -766,7 +791,7 @@ int b200_fa_decode_num_splits(int B, int Hkv, int max_context_len) {
 }
 
 int64_t b200_fa_decode_workspace_bytes(int B, int Hq, int Hkv, int D, int max_context_len, int num_splits) {
-  int splits = num_splits > 0 ? num_splits : b200_fa_decode_num_splits(B, Hkv, max_context_len);
+  int splits = num_splits > 0 ? num_splits : b200_fa_decode_num_splits(B, Hq, Hkv, D, max_context_len);
   if (splits <= 1) return 0;
   return static_cast<int64_t>(B) * Hq * splits * (D + 1) * static_cast<int64_t>(sizeof(float));
 }
@@ -795,7 +820,7 @@ int b200_fa_decode(const void* q, const void* k_cache, const void* v_cache, void
                        kv_batch_stride % 8 == 0,
                    "decode: bad contiguous-cache strides");
   }
-  int splits = num_splits > 0 ? num_splits : b200_fa_decode_num_splits(B, Hkv, max_context_len);
+  int splits = num_splits > 0 ? num_splits : b200_fa_decode_num_splits(B, Hq, Hkv, D, max_context_len);
   decode::Params p;
   p.q = q; p.k_cache = k_cache; p.v_cache = v_cache; p.o = o; p.lse = lse;
   p.part_o = nullptr; p.part_lse = nullptr;

@@ -282,7 +282,7 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
     scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
     lib = _lib.load()
     with torch.cuda.device(dev):
-        splits = num_splits if num_splits > 0 else lib.b200_fa_decode_num_splits(B, Hkv, max_context_len)
+        splits = num_splits if num_splits > 0 else lib.b200_fa_decode_num_splits(B, Hq, Hkv, D, max_context_len)
         ws_bytes = lib.b200_fa_decode_workspace_bytes(B, Hq, Hkv, D, max_context_len, splits)
         ws = _workspace(dev, ws_bytes)
         rc = lib.b200_fa_decode(q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), _ptr(lse), B, Hq,
