@@ -1205,13 +1205,19 @@ static int check_ptr16(const void* p, const char* name) {
 // (fewer output tiles than SMs) are split, into enough pieces to fill the machine, keeping >= 4 k-blocks per split
 static int choose_k_splits(int tiles, int kblocks, int64_t T, int n_blocks, int K) {
   const int sms = sm_count();
+  if (const char* e = getenv("B200_GEMM_K_SPLITS")) {  // developer knob (tests/gemm_split_probe.py): force the split count
+    const int s = atoi(e);
+    if (s >= 1) return s <= kblocks ? s : kblocks;
+  }
   if (tiles >= sms || kblocks < 8) return 1;
   // Skinny problems are weight-streaming bound and an SM can only pull so much: what matters is how many SMs stream at once.
-  // Cost model per candidate: bytes moved (weights + the fp32 partials written and re-read by the reduce pass) divided by
-  // the fraction of SM-waves that are full. (86 SwiGLU tiles of a T=64 Llama up-projection: 1 split = 58 % of the SMs,
-  // 5 splits = 430 CTAs = 2.9 waves = 97 %, for 56 MB of partials next to 180 MB of weights.)
+  // Cost model per candidate: bytes moved (weights + the fp32 partials, weighted) divided by the fraction of SM-waves that
+  // are full. The weight of the partials (3x their write + read bytes: they also cost the reduce launch and its latency)
+  // is fitted to tests/gemm_split_probe.py (profiles/r2_gemm_splits.jsonl, CUDA-graph replay, weights streamed from HBM):
+  // 86 SwiGLU tiles of a Llama up-projection want 1 split at T=64 (37.9 us; 3 splits 42.3 us: 17 MB of partials) but 5 at
+  // T=8 (37.4 vs 44.8 us: 3.5 MB); 16 tiles of the down projection want 9 (25.4 vs 65 us), 48 tiles of a QKV projection 3.
   const double w_bytes = static_cast<double>(n_blocks) * gemm::BN * K * 2.0;
-  const double part_bytes = 2.0 * static_cast<double>(T) * n_blocks * gemm::BN * 4.0;
+  const double part_bytes = 3.0 * 2.0 * static_cast<double>(T) * n_blocks * gemm::BN * 4.0;
   int best = 1;
   double best_cost = 1e300;
   for (int s = 1; s <= 32 && kblocks / s >= 4; ++s) {
