@@ -475,8 +475,12 @@ constexpr int P_SMEM_BAR_OFF = P_SMEM_C_OFF + 2 * C_BUF_BYTES;
 constexpr int P_SMEM_BYTES = P_SMEM_BAR_OFF + 256 + 1024;
 }  // namespace pair
 
-template <int ACT, typename T>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// EPI = number of epilogue warpgroups (1 or 2). With two, warpgroup e takes the 64-column chunks e, e + 2 of every tile
+// and owns one of the two staging buffers: for short K with a GELU (GPT-2 fc1: 12 k-blocks, 6144 MMA cycles per tile) the
+// epilogue of a 256-column tile is as long as the tile's MMAs, so one warpgroup makes the kernel epilogue-bound
+// (tests/gemm_epilogue_probe.py: 1259 TFLOP/s with GELU vs 1470 without).
+template <int ACT, typename T, int EPI = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * EPI, 1)
 gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b0,
                      const __grid_constant__ CUtensorMap tmap_b1, const __grid_constant__ CUtensorMap tmap_c,
                      const Params p) {
@@ -511,7 +515,7 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);   // multicast tcgen05.commit from the leader
-      mbar_init(&tmem_empty_bar[s], 2);  // leader's: one elected arrival per CTA of the pair
+      mbar_init(&tmem_empty_bar[s], 2 * EPI);  // leader's: one elected arrival per epilogue warpgroup of either CTA
     }
     fence_barrier_init();
   }
@@ -592,14 +596,19 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       }
     }
   } else if (warp_idx >= 4) {
-    // ===================== epilogue (both CTAs, own 128 rows) =====================
-    const int ep_warp = warp_idx - 4;
-    const int ep_tid = threadIdx.x - 128;
+    // ===================== epilogue (both CTAs, own 128 rows; EPI warpgroups) =====================
+    static_assert(EPI == 1 || EPI == 2, "one or two epilogue warpgroups");
+    const int wg = (warp_idx - 4) >> 2;            // epilogue warpgroup
+    const int ep_warp = (warp_idx - 4) & 3;        // TMEM lane quadrant
+    const int ep_tid = threadIdx.x - 128 - wg * 128;
     const int row = ep_warp * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(ep_warp * 32) << 16;
+    const uint32_t bar_chunk = 1u + static_cast<uint32_t>(wg), bar_done = 3u + static_cast<uint32_t>(wg);  // named barriers of this warpgroup
+    constexpr int kChunks = OUT_COLS / 64;
+    constexpr int kLastChunk0 = kChunks - EPI;     // the last chunk of warpgroup 0 (warpgroup e: + e)
     int acc = 0;
     uint32_t acc_phase = 0;
-    int cbuf = 0;
+    int cbuf = EPI == 2 ? wg : 0;                  // two warpgroups: one staging buffer each; one: both, alternating
     for (int tile = pair_id; tile < p.num_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       coords(tile, m_blk, n_blk);
@@ -609,10 +618,13 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tc_fence_after();
       const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int chunk = 0; chunk < OUT_COLS / 64; ++chunk) {
+      for (int chunk = wg; chunk < kChunks; chunk += EPI) {
         uint8_t* cs = smem + P_SMEM_C_OFF + cbuf * C_BUF_BYTES;
-        if (ep_tid == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
+        if (ep_tid == 0) {
+          if constexpr (EPI == 2) tma_store_wait_read<0>();   // this warpgroup's only buffer: its last store has been read
+          else tma_store_wait_read<1>();
+        }
+        named_bar_sync(bar_chunk, 128);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int col = chunk * 64 + half * 32;
@@ -635,10 +647,10 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             load_bias32<T>(p.bias0, n0 + col, p.N_out, b);
             bias_act32<ACT>(v, b, f);
           }
-          if (chunk == OUT_COLS / 64 - 1 && half == 1) {
-            // all TMEM reads of this accumulator stage are done in this CTA: one elected arrival on the leader's barrier
+          if (chunk == kLastChunk0 + wg && half == 1) {
+            // all TMEM reads of this accumulator stage by this warpgroup are done: one elected arrival on the leader's barrier
             tc_fence_before();
-            named_bar_sync(2, 128);
+            named_bar_sync(bar_done, 128);
             if (ep_tid == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
           }
 #pragma unroll
@@ -653,12 +665,12 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_chunk, 128);
         if (ep_tid == 0) {
           tma_store_2d_hint(&tmap_c, cs, n0 + chunk * 64, m0, p.hint_c);
           tma_store_commit();
         }
-        cbuf ^= 1;
+        if constexpr (EPI == 1) cbuf ^= 1;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -673,10 +685,16 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
 }
 
-template <int ACT, typename T>
+template <int ACT, typename T, int EPI = 1>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap& tb1, const CUtensorMap& tc, const Params& p,
                 cudaStream_t stream) {
-  auto kern = gemm_act_pair_kernel<ACT, T>;
+  if constexpr (EPI == 1 && (ACT == B200_ACT_GELU_TANH || ACT == B200_ACT_GELU_ERF)) {
+    // short K with a GELU: the epilogue of a tile is as long as its MMAs -> two epilogue warpgroups (B200_GEMM_EPI_WGS=1/2 forces)
+    const char* e = getenv("B200_GEMM_EPI_WGS");
+    const bool two = e != nullptr ? e[0] == '2' : p.num_k_blocks <= 16;
+    if (two) return launch_pair<ACT, T, 2>(ta, tb0, tb1, tc, p, stream);
+  }
+  auto kern = gemm_act_pair_kernel<ACT, T, EPI>;
   static bool attr_set[64] = {};  // per device
   B200_CUDA_OK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), pair::P_SMEM_BYTES, attr_set));
   int max_ctas = sm_count();
@@ -684,11 +702,13 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tb0, const CUtensorMap
   int pairs = max_ctas / 2;
   if (pairs > p.num_tiles) pairs = p.num_tiles;
   if (pairs < 1) pairs = 1;
-  kern<<<2 * pairs, NUM_THREADS, pair::P_SMEM_BYTES, stream>>>(ta, tb0, tb1, tc, p);
+  kern<<<2 * pairs, 128 + 128 * EPI, pair::P_SMEM_BYTES, stream>>>(ta, tb0, tb1, tc, p);
   B200_CUDA_OK(cudaGetLastError());
   static const char* const names[5] = {"gemm_act_pair_kernel<NONE>", "gemm_act_pair_kernel<GELU_TANH>", "gemm_act_pair_kernel<GELU_ERF>",
                                        "gemm_act_pair_kernel<RELU>", "gemm_act_pair_kernel<SWIGLU>"};
-  note_launch(names[ACT], true);
+  static const char* const names2[5] = {"gemm_act_pair_kernel<NONE,2wg>", "gemm_act_pair_kernel<GELU_TANH,2wg>", "gemm_act_pair_kernel<GELU_ERF,2wg>",
+                                        "gemm_act_pair_kernel<RELU,2wg>", "gemm_act_pair_kernel<SWIGLU,2wg>"};
+  note_launch(EPI == 2 ? names2[ACT] : names[ACT], true);
   return B200_OK;
 }
 
