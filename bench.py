@@ -628,8 +628,10 @@ def secondary_leg(cx, args):
     torch.cuda.empty_cache()
 
     # ---- isolated causal attention: C3 / C2 shapes ----
-    for tag, (B, S, H, D) in (("attn_c3_causal", (4, 8192, 32, 128)), ("attn_c2_causal", (8, 4096, 12, 64))):
-        q, k, v = (torch.randn(B, S, H, D, device=dev, dtype=bf) for _ in range(3))
+    for tag, (B, S, H, D), Hkv in (("attn_c3_causal", (4, 8192, 32, 128), 32), ("attn_c4_gqa_causal", (4, 8192, 32, 128), 8),
+                                   ("attn_c2_causal", (8, 4096, 12, 64), 12)):
+        q = torch.randn(B, S, H, D, device=dev, dtype=bf)
+        k, v = (torch.randn(B, S, Hkv, D, device=dev, dtype=bf) for _ in range(2))
         o = torch.empty_like(q)
         ms = cx.timed(lambda: ops.flash_attn_fwd(q, k, v, causal=True, out=o), 3, 10)
         fl = 4.0 * B * H * S * S * D * 0.5
@@ -637,6 +639,8 @@ def secondary_leg(cx, args):
         try:  # same-GPU comparator: cuDNN SDPA
             from torch.nn.attention import SDPBackend, sdpa_kernel
             qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))
+            if Hkv != H:  # the comparator gets K/V already expanded to the query heads (no GQA saving on its side)
+                kt, vt = (t.repeat_interleave(H // Hkv, dim=1) for t in (kt, vt))
             with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
                 ms_c = cx.timed(lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=True), 3, 10)
             rec["cudnn_sdpa_tflops"] = fl / ms_c / 1e9
