@@ -284,25 +284,28 @@ constexpr bool kGqaRingDefault = false;
 // (D = 128: 128 of ~250 registers -> 2 CTAs; D = 64: 64 of ~170 -> 3 CTAs, measured 4721 vs 4002 GB/s with 2)
 template <int D> struct GqaMinCtas { static constexpr int value = D == 128 ? 2 : 3; };
 
-// RING = true: every warp owns a ring of GQA_RING_STAGES K/V tiles in shared memory, filled by one 256-byte
-// cp.async.bulk per key row (lanes 0-15: K rows, lanes 16-31: V rows) that completes on the stage's mbarrier; the MMA
-// fragments are then read with conflict-free 128-bit shared loads (row pitches D*2+64 for K and D*2+16 for V). Two tiles
-// per warp are in flight while a third is being consumed (RING = false keeps one tile in flight in registers), and the
-// staging registers shrink from 128 to 64 per lane. The combine buffers of the epilogue alias the ring.
+// RING = true: every warp stages its K/V tiles through a private ring in shared memory instead of registers: each lane
+// issues the same 16-byte pieces it would have loaded (cp.async.cg, zero-filled for keys past the end) into its own
+// 16-byte column of a [slot][lane] array — no lane ever reads another lane's bytes, so there is no layout, bank-conflict or
+// synchronisation question — and reads them back as MMA fragments when the tile's copy group has completed. Two tiles per
+// warp are in flight while a third is consumed (the register-staged variant keeps one), and the staging registers go
+// from 128 to 64 per lane. The combine buffers of the epilogue alias the ring. (A first version used one 256-byte
+// cp.async.bulk per key row and mbarriers: slower, 5309 vs 5810 GB/s — 32 small bulk copies per 8 KB tile.)
 constexpr int GQA_RING_STAGES = 3;
 template <int D> struct GqaRing {
-  static constexpr int KP = D * 2 + 64, VP = D * 2 + 16;          // row pitches in bytes
-  static constexpr int TILE_BYTES = 16 * KP + 16 * VP;
+  static constexpr int SLOTS = 2 * (D / 32) + (D / 64) * 4;       // 16-byte pieces per lane and tile (K: 2 x MB, V: DG x 4)
+  static constexpr int TILE_BYTES = SLOTS * 32 * 16;              // 8 KB at D = 128
   static constexpr int RING_BYTES = GQA_WARPS * GQA_RING_STAGES * TILE_BYTES;
-  static constexpr int BAR_OFF = RING_BYTES;
   static constexpr int COMB_BYTES = (2 * GQA_WARPS * 16 + GQA_WARPS * 16 * D) * 4;
-  static constexpr int SMEM_BYTES = (RING_BYTES + GQA_WARPS * GQA_RING_STAGES * 8 > COMB_BYTES ? RING_BYTES + GQA_WARPS * GQA_RING_STAGES * 8 : COMB_BYTES);
+  static constexpr int SMEM_BYTES = RING_BYTES > COMB_BYTES ? RING_BYTES : COMB_BYTES;
 };
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar_smem) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
-               "r"(bytes), "r"(bar_smem)
-               : "memory");
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination (keys past the end of the sequence)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 r;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -442,55 +445,51 @@ decode_gqa_mma_kernel(const Params p, const int G) {
   if constexpr (RING) {
     using R = GqaRing<D>;
     constexpr int NSTG = GQA_RING_STAGES;
-    const uint32_t ring0 = smem_u32(gqa_dsm) + static_cast<uint32_t>(warp * NSTG * R::TILE_BYTES);
-    const uint32_t bar0 = smem_u32(gqa_dsm) + static_cast<uint32_t>(R::BAR_OFF + warp * NSTG * 8);
-    if (lane == 0) {
-#pragma unroll
-      for (int sidx = 0; sidx < NSTG; ++sidx) mbar_init(reinterpret_cast<uint64_t*>(gqa_dsm + R::BAR_OFF + (warp * NSTG + sidx) * 8), 1);
-      fence_barrier_init();
-    }
-    __syncwarp();
+    // this lane's 16-byte column of slot 0 of stage 0
+    const uint32_t ring0 = smem_u32(gqa_dsm) + static_cast<uint32_t>(warp * NSTG * R::TILE_BYTES + lane * 16);
     const int first_t0 = k_begin + warp * TILE;
     const int n_tiles = first_t0 < k_end ? (k_end - first_t0 + STEP - 1) / STEP : 0;
-    // tile i of this warp -> stage i % NSTG: lanes 0-15 copy the K rows, lanes 16-31 the V rows (256 bytes each at D = 128)
-    auto issue_ring = [&](const int i) {
-      const int t0 = first_t0 + i * STEP, stage = i % NSTG;
-      const int nvalid = min(TILE, k_end - t0);
-      const uint32_t bar = bar0 + static_cast<uint32_t>(stage * 8);
-      __syncwarp();  // every lane has finished reading the tile that lived in this stage
-      if (lane == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(static_cast<uint32_t>(nvalid * 2 * D * 2)) : "memory");
+    auto issue_ring = [&](const int i) {  // tile i of this warp -> stage i % NSTG (one commit group, possibly empty)
+      if (i < n_tiles) {
+        const int t0 = first_t0 + i * STEP;
+        const uint32_t st = ring0 + static_cast<uint32_t>((i % NSTG) * R::TILE_BYTES);
+#pragma unroll
+        for (int kg = 0; kg < 2; ++kg) {
+          const int key = t0 + kg * 8 + g;
+          const bool valid = key < k_end;
+          const T* src = kc + (valid ? row_offset(key) + 8 * t : 0);
+#pragma unroll
+          for (int m = 0; m < MB; ++m) cp_async16(st + static_cast<uint32_t>((kg * MB + m) * 512), src + 32 * m, valid ? 16u : 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int key = t0 + 2 * t + (j & 1) + (j >> 1) * 8;
+          const bool valid = key < k_end;
+          const T* src = vc + (valid ? row_offset(key) + 8 * g : 0);
+#pragma unroll
+          for (int d = 0; d < DG; ++d) cp_async16(st + static_cast<uint32_t>((2 * MB + d * 4 + j) * 512), src + 64 * d, valid ? 16u : 0u);
+        }
       }
-      __syncwarp();
-      const int r = lane & 15;
-      if (r < nvalid) {
-        const bool is_v = lane >= 16;
-        const T* src = (is_v ? vc : kc) + row_offset(t0 + r);
-        const uint32_t dst = ring0 + static_cast<uint32_t>(stage * R::TILE_BYTES + (is_v ? 16 * R::KP + r * R::VP : r * R::KP));
-        bulk_copy_g2s(dst, src, D * 2, bar);
-      }
+      cp_async_commit();
     };
-    for (int i = 0; i < NSTG - 1 && i < n_tiles; ++i) issue_ring(i);
+#pragma unroll
+    for (int i = 0; i < NSTG - 1; ++i) issue_ring(i);
     for (int i = 0; i < n_tiles; ++i) {
-      if (i + NSTG - 1 < n_tiles) issue_ring(i + NSTG - 1);
-      const int t0 = first_t0 + i * STEP, stage = i % NSTG;
-      mbar_wait_addr(bar0 + static_cast<uint32_t>(stage * 8), static_cast<uint32_t>((i / NSTG) & 1));
-      const uint32_t kb = ring0 + static_cast<uint32_t>(stage * R::TILE_BYTES), vb = kb + 16 * R::KP;
+      issue_ring(i + NSTG - 1);          // refills the stage consumed in iteration i - 1 (its fragments are in registers)
+      cp_async_wait<NSTG - 1>();         // all groups but the NSTG - 1 most recent are complete: tile i has landed
+      const uint32_t st = ring0 + static_cast<uint32_t>((i % NSTG) * R::TILE_BYTES);
       uint4 kr[2][MB], vr[DG][4];
 #pragma unroll
       for (int kg = 0; kg < 2; ++kg)
 #pragma unroll
-        for (int m = 0; m < MB; ++m) kr[kg][m] = lds128(kb + static_cast<uint32_t>((kg * 8 + g) * R::KP + (8 * t + 32 * m) * 2));
+        for (int m = 0; m < MB; ++m) kr[kg][m] = lds128(st + static_cast<uint32_t>((kg * MB + m) * 512));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int kr_ = 2 * t + (j & 1) + (j >> 1) * 8;
-        const bool valid = t0 + kr_ < k_end;  // rows past the end were not copied: they must read as zeros (0 x NaN)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int d = 0; d < DG; ++d)
-          vr[d][j] = valid ? lds128(vb + static_cast<uint32_t>(kr_ * R::VP + (8 * g + 64 * d) * 2)) : make_uint4(0, 0, 0, 0);
-      }
-      compute_tile(t0, kr, vr);
+        for (int d = 0; d < DG; ++d) vr[d][j] = lds128(st + static_cast<uint32_t>((2 * MB + d * 4 + j) * 512));
+      compute_tile(first_t0 + i * STEP, kr, vr);
     }
+    cp_async_wait<0>();
     __syncthreads();  // the combine buffers below alias the ring
   } else {
     uint4 krA[2][MB], vrA[DG][4], krB[2][MB], vrB[DG][4];

@@ -299,9 +299,9 @@ def test_decode_contiguous_vs_oracle(ops, B, Hq, Hkv, D, S, splits):
 
 @pytest.mark.parametrize("B,Hq,Hkv,D,S,splits", [c for c in DECODE_CASES if c[1] // c[2] >= 3])
 def test_decode_gqa_ring_variant_vs_oracle(ops, monkeypatch, B, Hq, Hkv, D, S, splits):
-    """The shared-memory-ring variant of the GQA decode kernel (B200_GQA_RING=1: per-warp cp.async.bulk ring, fragments read
+    """The shared-memory-ring variant of the GQA decode kernel (B200_GQA_RING=1: per-lane cp.async staging, fragments read
     back with 128-bit shared loads; measured slower than the register-staged default, kept as an option) — same results,
-    including tiles whose last rows were never copied."""
+    including tiles whose last rows are zero-filled."""
     monkeypatch.setenv("B200_GQA_RING", "1")
     g = torch.Generator(device="cuda").manual_seed(1)
     q = torch.randn(B, Hq, D, device="cuda", dtype=torch.bfloat16, generator=g)
