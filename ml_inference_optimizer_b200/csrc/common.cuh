@@ -51,6 +51,12 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Same with the barrier id as an immediate: with a run-time id ptxas reserves all 16 hardware barriers for the CTA, which
+// can keep another kernel's CTAs (the co-resident tensor-parallel all-reduce) off the SM.
+template <int ID>
+__device__ __forceinline__ void named_bar_sync_imm(uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

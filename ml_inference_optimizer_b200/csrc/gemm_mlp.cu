@@ -598,12 +598,20 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else if (warp_idx >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows; EPI warpgroups) =====================
     static_assert(EPI == 1 || EPI == 2, "one or two epilogue warpgroups");
-    const int wg = (warp_idx - 4) >> 2;            // epilogue warpgroup
+    const int wg = EPI == 1 ? 0 : ((warp_idx - 4) >> 2);   // epilogue warpgroup (a compile-time 0 with one: keeps that build at 209 registers)
     const int ep_warp = (warp_idx - 4) & 3;        // TMEM lane quadrant
     const int ep_tid = threadIdx.x - 128 - wg * 128;
     const int row = ep_warp * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(ep_warp * 32) << 16;
-    const uint32_t bar_chunk = 1u + static_cast<uint32_t>(wg), bar_done = 3u + static_cast<uint32_t>(wg);  // named barriers of this warpgroup
+    // named barriers of this warpgroup, ids as immediates (1, 2 with one warpgroup as before; 1-4 with two)
+    auto sync_chunk = [&]() {
+      if (EPI == 1 || wg == 0) named_bar_sync_imm<1>(128);
+      else named_bar_sync_imm<3>(128);
+    };
+    auto sync_done = [&]() {
+      if (EPI == 1 || wg == 0) named_bar_sync_imm<2>(128);
+      else named_bar_sync_imm<4>(128);
+    };
     constexpr int kChunks = OUT_COLS / 64;
     constexpr int kLastChunk0 = kChunks - EPI;     // the last chunk of warpgroup 0 (warpgroup e: + e)
     int acc = 0;
@@ -624,7 +632,7 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if constexpr (EPI == 2) tma_store_wait_read<0>();   // this warpgroup's only buffer: its last store has been read
           else tma_store_wait_read<1>();
         }
-        named_bar_sync(bar_chunk, 128);
+        sync_chunk();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int col = chunk * 64 + half * 32;
@@ -650,7 +658,7 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (chunk == kLastChunk0 + wg && half == 1) {
             // all TMEM reads of this accumulator stage by this warpgroup are done: one elected arrival on the leader's barrier
             tc_fence_before();
-            named_bar_sync(bar_done, 128);
+            sync_done();
             if (ep_tid == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
           }
 #pragma unroll
@@ -665,7 +673,7 @@ gemm_act_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(bar_chunk, 128);
+        sync_chunk();
         if (ep_tid == 0) {
           tma_store_2d_hint(&tmap_c, cs, n0 + chunk * 64, m0, p.hint_c);
           tma_store_commit();

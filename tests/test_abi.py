@@ -111,3 +111,35 @@ def test_lib_path_override_is_explicit(monkeypatch, tmp_path):
     monkeypatch.delenv("B200_LIB_PATH")
     monkeypatch.setattr(L, "_lib", None)
     assert L.load() is not None
+
+
+def test_co_residency_budget_of_the_tensor_parallel_overlap(built_lib):
+    """The in-switch all-reduce CTAs (K6) are meant to run UNDERNEATH the persistent GEMM CTAs of the next token chunk: on
+    one SM, 256 GEMM threads + 256 all-reduce threads must fit the 64K registers (allocation granularity 8 per thread). A
+    refactor that silently grows the GEMM kernel's registers (it happened: 209 -> 250 cost 0.45 ms of a 4.3 ms TP step) or
+    makes it reserve all 16 named barriers breaks the overlap without failing any numerical test — so it is checked here."""
+    import shutil
+    import subprocess
+
+    from ml_inference_optimizer_b200 import build as b
+
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", str(b.LIB_PATH)], capture_output=True, text=True).stdout
+    regs = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    up8 = lambda r: (r + 7) // 8 * 8
+    gemm = {k: v for k, v in regs.items() if "gemm_act_pair_kernelILi4E" in k or "gemm_act_pair_kernelILi0E" in k}
+    gemm = {k: v for k, v in gemm.items() if "Li1EEE" in k}          # the one-epilogue-warpgroup builds the TP path launches
+    ar = {k: v for k, v in regs.items() if "tp_allreduce_kernel" in k}
+    assert gemm and ar, "kernels not found in the library"
+    worst = max(up8(g) for g in gemm.values()) * 256 + max(up8(a) for a in ar.values()) * 256
+    assert worst <= 65536, (gemm, ar)
