@@ -143,3 +143,23 @@ def test_co_residency_budget_of_the_tensor_parallel_overlap(built_lib):
     assert gemm and ar, "kernels not found in the library"
     worst = max(up8(g) for g in gemm.values()) * 256 + max(up8(a) for a in ar.values()) * 256
     assert worst <= 65536, (gemm, ar)
+
+
+def test_measured_heuristics_are_pinned(built_lib):
+    """The split rules were fitted to sweeps on the GPU (profiles/r2_decode_splits.jsonl, profiles/r2_gemm_splits.jsonl);
+    these are the choices the sweeps found best, pinned so that a later edit of the rules has to look at the data again.
+    (Pure host functions: 148 SMs are assumed when no device is present.)"""
+    ns = built_lib.b200_fa_decode_num_splits
+    #        B  Hq Hkv   D  context                                  measured optimum
+    assert ns(32, 16, 1, 128, 8192) == 8      # MQA, 32 CTAs per split: one wave of 256 CTAs (46 us vs 79 us at 32 splits)
+    assert ns(8, 32, 8, 128, 8192) == 4       # 64 x 4 = 256 CTAs (64 us; 5 splits = 1.08 waves: 89 us)
+    assert ns(1, 32, 8, 128, 32768) == 32
+    assert ns(64, 32, 8, 128, 8192) == 4      # C4: 512 CTAs = 1.73 waves -> 4 splits fill the last wave
+    assert ns(64, 32, 32, 128, 8192) == 1     # C3 MHA: 2048 CTAs, never split
+    assert ns(64, 16, 4, 64, 8192) == 8       # D = 64 GQA (3 CTAs per SM): under-filled single wave, bandwidth-sized -> several waves
+    assert ns(1, 12, 12, 64, 64) == 1         # GPT-2 decode at short context: >= 256 keys per split
+    ws = built_lib.b200_linear_act_workspace_bytes
+    assert ws(64, 4096, 11008, 4) == 0                                  # SwiGLU up+gate at T=64: 86 tiles, no split (37.9 vs 42.3 us)
+    assert ws(64, 11008, 4096, 0) == 9 * 64 * 16 * 256 * 4              # down projection at T=64: 16 tiles x 9 splits
+    assert ws(8, 4096, 11008, 4) == 5 * 8 * 86 * 256 * 4                # T=8: small partials -> 5 splits (37.4 vs 44.8 us)
+    assert ws(32768, 4096, 11008, 4) == 0                               # prefill: never split
