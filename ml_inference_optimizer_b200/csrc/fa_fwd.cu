@@ -66,6 +66,9 @@ struct Params {
   float* lse;               // [B, Hq, Sq] or nullptr
   const int32_t* kv_lens;   // [B] or nullptr
   int B, Sq, Sk, Hq, Hkv;
+  int d_real;               // head_dim of the tensors (a multiple of 8, <= the kernel's D): the TMA loads zero-fill the columns
+                            // [d_real, D) of Q / K / V (exact: they add 0 to every score and produce 0 outputs) and the
+                            // epilogue does not store them
   float scale_log2;         // softmax_scale * log2(e)
   int causal;
   int64_t causal_offset;    // key j visible to query i iff j <= i + causal_offset
@@ -583,7 +586,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
                 pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
                 pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
-                *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
+                if (c * 32 + q4 * 8 < p.d_real) *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
               }
             }
           }
@@ -627,6 +630,7 @@ fa_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             if (touch) {
 #pragma unroll
               for (int q4 = 0; q4 < 8; ++q4) {
+                if (c * 32 + q4 * 4 >= p.d_real) continue;
                 float4* dst = reinterpret_cast<float4*>(arow + c * 32 + q4 * 4);
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (!p.acc_init) a = *dst;
@@ -1085,7 +1089,7 @@ fa_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
               pk.y = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 2]) * inv_l, __uint_as_float(o[q4 * 8 + 3]) * inv_l);
               pk.z = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 4]) * inv_l, __uint_as_float(o[q4 * 8 + 5]) * inv_l);
               pk.w = Pack2<T>::pack(__uint_as_float(o[q4 * 8 + 6]) * inv_l, __uint_as_float(o[q4 * 8 + 7]) * inv_l);
-              *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
+              if (w * (D / 2) + c * 32 + q4 * 8 < p.d_real) *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = pk;
             }
           }
         }
@@ -1124,6 +1128,7 @@ fa_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           if (touch) {
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
+              if (w * (D / 2) + c * 32 + q4 * 4 >= p.d_real) continue;
               float4* dst = reinterpret_cast<float4*>(arow + c * 32 + q4 * 4);
               float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
               if (!p.acc_init) a = *dst;
@@ -1195,7 +1200,11 @@ static int run(const void* q, const void* k, const void* v, int B, int Sq, int S
   B200_CHECK_ARG(B > 0 && Sq > 0 && Sk > 0 && Hq > 0 && Hkv > 0, "fa_fwd: bad sizes B=%d Sq=%d Sk=%d Hq=%d Hkv=%d", B, Sq,
                  Sk, Hq, Hkv);
   B200_CHECK_ARG(Hq % Hkv == 0, "fa_fwd: Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
-  B200_CHECK_ARG(D == 64 || D == 128, "fa_fwd: head_dim %d unsupported (64, 128)", D);
+  // head_dim: any multiple of 8 up to 128 (reference: hidden_size // num_heads, unconstrained). The kernels are built for
+  // 64 and 128 columns; a narrower head runs in the next wider build with its missing columns zero-filled by TMA.
+  B200_CHECK_ARG(D >= 8 && D <= 128 && D % 8 == 0, "fa_fwd: head_dim %d unsupported (a multiple of 8, at most 128)", D);
+  p.d_real = D;
+  const int KD = D <= 64 ? 64 : 128;  // the kernel build
   B200_CHECK_ARG(dtype == B200_DTYPE_BF16 || dtype == B200_DTYPE_FP16, "fa_fwd: dtype must be bf16 or fp16");
   B200_CHECK_ARG(softmax_scale > 0.f, "fa_fwd: softmax_scale must be positive");
   B200_CHECK_ARG(B <= 65535 && Hq <= 65535, "fa_fwd: B and Hq must be <= 65535");
@@ -1235,17 +1244,17 @@ static int run(const void* q, const void* k, const void* v, int B, int Sq, int S
   const bool bf = dtype == B200_DTYPE_BF16;
   if (use_pair) {
     if (accum) {
-      if (D == 128) return bf ? launch_pair<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch_pair<128, __half, true>(tq, tk, tv, p, s);
+      if (KD == 128) return bf ? launch_pair<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch_pair<128, __half, true>(tq, tk, tv, p, s);
       return bf ? launch_pair<64, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch_pair<64, __half, true>(tq, tk, tv, p, s);
     }
-    if (D == 128) return bf ? launch_pair<128, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch_pair<128, __half, false>(tq, tk, tv, p, s);
+    if (KD == 128) return bf ? launch_pair<128, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch_pair<128, __half, false>(tq, tk, tv, p, s);
     return bf ? launch_pair<64, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch_pair<64, __half, false>(tq, tk, tv, p, s);
   }
   if (accum) {
-    if (D == 128) return bf ? launch<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<128, __half, true>(tq, tk, tv, p, s);
+    if (KD == 128) return bf ? launch<128, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<128, __half, true>(tq, tk, tv, p, s);
     return bf ? launch<64, __nv_bfloat16, true>(tq, tk, tv, p, s) : launch<64, __half, true>(tq, tk, tv, p, s);
   }
-  if (D == 128) return bf ? launch<128, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch<128, __half, false>(tq, tk, tv, p, s);
+  if (KD == 128) return bf ? launch<128, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch<128, __half, false>(tq, tk, tv, p, s);
   return bf ? launch<64, __nv_bfloat16, false>(tq, tk, tv, p, s) : launch<64, __half, false>(tq, tk, tv, p, s);
 }
 
@@ -1304,6 +1313,7 @@ extern "C" int b200_fa_fwd_paged(const void* q, const void* k_cache, const void*
                  "fa_fwd_paged: block_size %d must be a power of two in [8, 128]", block_size);
   B200_CHECK_ARG(max_blocks_per_seq > 0 && num_blocks > 0 && num_layers > 0 && layer_idx >= 0 && layer_idx < num_layers,
                  "fa_fwd_paged: bad paged-cache arguments");
+  B200_CHECK_ARG(D == 64 || D == 128, "fa_fwd_paged: head_dim %d unsupported (the paged cache holds 64 or 128)", D);
   for (int i = 0; i < 3; ++i)
     B200_CHECK_ARG(o_strides[i] > 0 && o_strides[i] % 8 == 0, "fa_fwd_paged: o stride %d = %lld must be a positive multiple of 8 elements",
                    i, (long long)o_strides[i]);

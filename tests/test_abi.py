@@ -45,7 +45,7 @@ def test_invalid_arguments_return_error_codes(built_lib):
     dummy = ctypes.c_void_p(256)
     rc = built_lib.b200_fa_fwd(dummy, dummy, dummy, dummy, None, 1, 128, 128, 3, 2, 128, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
     assert rc == -1 and "multiple of Hkv" in _lib.last_error()
-    rc = built_lib.b200_fa_fwd(dummy, dummy, dummy, dummy, None, 1, 128, 128, 2, 2, 96, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
+    rc = built_lib.b200_fa_fwd(dummy, dummy, dummy, dummy, None, 1, 128, 128, 2, 2, 100, s3, s3, s3, s3, 0.1, 0, 0, None, 0, None)
     assert rc == -1 and "head_dim" in _lib.last_error()
     rc = built_lib.b200_linear_act(dummy, 60, dummy, None, None, None, dummy, 64, 8, 60, 64, 0, None, 0, 0, None)
     assert rc == -1 and "multiples of 8" in _lib.last_error()

@@ -42,12 +42,13 @@ def test_flash_attention3_module_masks_and_dtypes():
         FlashAttention3(FlashAttentionConfig(precision="fp8"))(q, k, v)
 
 
+@pytest.mark.parametrize("hidden,H,Hkv", [(512, 8, 2), (640, 8, 4), (384, 4, 4)])   # head_dim 64, 80 (Phi-2), 96
 @pytest.mark.parametrize("cls_name", ["FlashAttentionLayer", "FlashSelfAttention"])
-def test_attention_layers_vs_oracle(cls_name):
+def test_attention_layers_vs_oracle(cls_name, hidden, H, Hkv):
     import kernels.attention.flash_attention as fa
 
     torch.manual_seed(0)
-    hidden, H, Hkv, B, S = 512, 8, 2, 2, 320
+    B, S = 2, 320
     layer = getattr(fa, cls_name)(hidden, H, fa.FlashAttentionConfig(causal=True, precision="bf16"), num_kv_heads=Hkv)
     layer = layer.to("cuda", torch.bfloat16).eval()
     x = torch.randn(B, S, hidden, device="cuda", dtype=torch.bfloat16)

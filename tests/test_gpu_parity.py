@@ -83,6 +83,35 @@ def test_fa_fwd_vs_oracle(ops, B, Sq, Sk, Hq, Hkv, D, causal, offset, kv_lens):
     check_lse(lse, rl)
 
 
+@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("D", [8, 32, 40, 80, 96, 120])
+def test_fa_fwd_any_head_dim(ops, monkeypatch, D, pair):
+    """head_dim = any multiple of 8 up to 128 (the reference takes hidden_size // num_heads as it comes,
+    flash_attention.py:176): the 64- / 128-column builds run it with the missing columns zero-filled by the TMA loads, which is
+    exact, and the epilogue must not store past column D (guard columns next to every output row stay untouched). Both output
+    modes (16-bit and the fp32 accumulate of a ring step)."""
+    monkeypatch.setenv("B200_FA_PAIR", "1" if pair else "0")
+    B, Sq, Sk, Hq, Hkv = 2, 300, 520, 4, 2
+    q, k, v = rand_qkv(B, Sq, Sk, Hq, Hkv, D, seed=D)
+    big = torch.full((B, Sq, Hq, D + 8), -7.0, device="cuda", dtype=torch.bfloat16)
+    o, lse = ops.flash_attn_fwd(q, k, v, causal=True, causal_offset=Sk - Sq, return_lse=True, out=big[..., :D])
+    assert ops.last_kernel() == ("fa_fwd_pair_kernel" if pair else "fa_fwd_kernel")
+    ro, rl = orc.attention_ref(q.cpu(), k.cpu(), v.cpu(), causal=True, causal_offset=Sk - Sq)
+    check_out(o, ro)
+    check_lse(lse, rl)
+    assert (big[..., D:] == -7.0).all(), "columns past head_dim were written"
+    acc_big = torch.full((B, Sq, Hq, D + 8), -7.0, device="cuda", dtype=torch.float32)
+    lse_acc = torch.empty((B, Hq, Sq), device="cuda", dtype=torch.float32)
+    for i, (a, b) in enumerate(((0, 256), (256, Sk))):
+        ops.flash_attn_fwd_accum(q, k[:, a:b], v[:, a:b], acc_big[..., :D], lse_acc, init=(i == 0), causal=True,
+                                 causal_offset=Sk - Sq - a)
+    check_out(acc_big[..., :D], ro)
+    check_lse(lse_acc, rl)
+    assert (acc_big[..., D:] == -7.0).all()
+    with pytest.raises(RuntimeError, match="head_dim"):
+        ops.flash_attn_fwd(*rand_qkv(1, 128, 128, 1, 1, 136))
+
+
 PAIR_CASES = FA_CASES + [
     (2, 640, 640, 4, 2, 128, True, 0, None),         # odd number of 128-row tiles: the second CTA of the last cluster has no rows
     (1, 1536, 1536, 2, 2, 64, True, 0, [1000]),      # padding + causal, D = 64
