@@ -22,7 +22,7 @@ from ... import ops
 from ...parallelism.ring import ring_attention_forward
 
 __all__ = ["RingAttentionConfig", "RingAttention", "RingSelfAttention", "RingCrossAttention", "ModelConverter",
-           "benchmark_ring_attention", "calculate_theoretical_flops"]
+           "benchmark_ring_attention", "calculate_theoretical_flops", "compare_with_standard_attention"]
 
 
 @dataclass
@@ -199,21 +199,61 @@ def calculate_theoretical_flops(seq_len: int, batch_size: int, hidden_size: int,
     return qkv + scores + out + proj
 
 
-def benchmark_ring_attention(batch_size: int = 1, seq_len: int = 8192, hidden_size: int = 4096, num_heads: int = 32,
-                             causal: bool = True, num_iters: int = 10, warmup_iters: int = 3) -> Dict[str, float]:
-    """reference :838-918 — time the module forward on this rank's shard (CUDA events)."""
-    cfg = RingAttentionConfig(world_size=dist.get_world_size() if dist.is_initialized() else 1)
-    mod = RingSelfAttention(hidden_size, num_heads, cfg, causal=causal).to("cuda", torch.bfloat16)
-    x = torch.randn(batch_size, seq_len // cfg.world_size, hidden_size, device="cuda", dtype=torch.bfloat16)
-    for _ in range(warmup_iters):
-        mod(x)
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(num_iters):
-        mod(x)
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / num_iters
-    flops = 2 * calculate_theoretical_flops(seq_len, batch_size, hidden_size, num_heads) / cfg.world_size
-    return {"ms": ms, "tflops_per_gpu": flops / ms / 1e9, "world_size": cfg.world_size}
+def _standard_self_attention(mod: "RingSelfAttention", x: torch.Tensor, fp32: bool) -> torch.Tensor:
+    """Comparator of the helpers below: the same projections followed by materialised-score attention (``[B,H,S,S]``)."""
+    if fp32:
+        lin = lambda l, t: nn.functional.linear(t, l.weight.float(), l.bias.float())
+        x = x.float()
+    else:
+        lin = lambda l, t: l(t)
+    B, S, _ = x.shape
+    H, D = mod.num_attention_heads, mod.head_dim
+    if mod.config.fuse_qkv:
+        q, k, v = lin(mod.qkv_proj, x).split(mod.hidden_size, dim=-1)
+    else:
+        q, k, v = lin(mod.q_proj, x), lin(mod.k_proj, x), lin(mod.v_proj, x)
+    q, k, v = (t.view(B, S, H, D).transpose(1, 2) for t in (q, k, v))
+    scores = q @ k.transpose(-1, -2) / math.sqrt(D)
+    if mod.causal:
+        scores = scores.masked_fill(torch.ones(S, S, dtype=torch.bool, device=x.device).triu(1), float("-inf"))
+    ctx = (torch.softmax(scores.float(), dim=-1).to(v.dtype) @ v).transpose(1, 2).reshape(B, S, H * D)
+    return lin(mod.out_proj, ctx)
+
+
+def benchmark_ring_attention(seq_len: int = 8192, batch_size: int = 1, hidden_size: int = 4096, num_heads: int = 32,
+                             causal: bool = False, num_iters: int = 10, warmup_iters: int = 3) -> Dict[str, float]:
+    """reference :838-918 (same positional arguments and result keys) — the module forward on this rank's shard next to
+    materialised-score attention with the same weights, CUDA events and peak memory. The comparator runs on a single
+    process while its score matrix stays under 16 GB; beyond that its entries are NaN."""
+    from .. import _measure as M
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    cfg = RingAttentionConfig(world_size=world)
+    mod = RingSelfAttention(hidden_size, num_heads, cfg, causal=causal).to("cuda", torch.bfloat16).eval()
+    x = torch.randn(batch_size, seq_len // world, hidden_size, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        ring_mem, _ = M.peak_mb(lambda: mod(x))
+        ms = M.time_ms(lambda: mod(x), warmup_iters, num_iters)
+        std_ms = std_mem = float("nan")
+        if world == 1 and batch_size * num_heads * seq_len * seq_len * 6 <= 16 * 2 ** 30:
+            std_mem, _ = M.peak_mb(lambda: _standard_self_attention(mod, x, False))
+            std_ms = M.time_ms(lambda: _standard_self_attention(mod, x, False), 1, max(1, min(num_iters, 5)))
+    flops = 2 * calculate_theoretical_flops(seq_len, batch_size, hidden_size, num_heads) / world
+    return {"standard_time_ms": std_ms, "ring_time_ms": ms, "speedup_factor": std_ms / ms, "standard_memory_mb": std_mem,
+            "ring_memory_mb": ring_mem, "memory_savings_factor": std_mem / max(ring_mem, 1e-6),
+            "ms": ms, "tflops_per_gpu": flops / ms / 1e9, "world_size": world}
+
+
+def compare_with_standard_attention(seq_len: int, batch_size: int, hidden_size: int, num_heads: int) -> Dict[str, float]:
+    """reference :958-1040 — RingSelfAttention (separate q/k/v projections, one process) against materialised-score
+    attention computed in fp32 with the same weights, followed by the benchmark above."""
+    cfg = RingAttentionConfig(world_size=1, fuse_qkv=False)
+    torch.manual_seed(0)
+    mod = RingSelfAttention(hidden_size, num_heads, cfg).to("cuda", torch.bfloat16).eval()
+    x = torch.randn(batch_size, seq_len, hidden_size, device="cuda", dtype=torch.bfloat16)
+    with torch.no_grad():
+        err = (mod(x).float() - _standard_self_attention(mod, x, True)).abs()
+        ref_mean = _standard_self_attention(mod, x, True).abs().mean().item()
+    return {"max_absolute_diff": err.max().item(), "mean_absolute_diff": err.mean().item(),
+            "relative_error": err.mean().item() / max(ref_mean, 1e-12),
+            **benchmark_ring_attention(seq_len, batch_size, hidden_size, num_heads)}

@@ -2,11 +2,13 @@
 single-GPU "ring" (chunked online-softmax) attention."""
 from __future__ import annotations
 
-from typing import Optional
+import math
+from typing import Dict, Optional
 
 import torch
 
 from ... import ops
+from .. import _measure as M
 
 TRITON_AVAILABLE = True
 
@@ -52,3 +54,48 @@ def triton_ring_attention_forward(query: torch.Tensor, key: torch.Tensor, value:
     B, H, S, D = query.shape
     o = ops.flash_attn_fwd(query.transpose(1, 2), key.transpose(1, 2), value.transpose(1, 2))
     return o.reshape(B, S, H * D)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's own measurement helpers for this file (:1643-1800), same arguments and result keys.
+# ------------------------------------------------------------------------------------------------------------------
+def compare_with_flash_attention(seq_len: int, batch_size: int, hidden_size: int, num_heads: int) -> Dict[str, float]:
+    """reference :1643-1732 — ``triton_ring_attention_forward`` next to the ``flash_attn`` package's kernel (fp16, non-causal).
+    Returns ``{"error": ...}`` when that package cannot be imported or cannot run on this GPU, as the reference does."""
+    try:
+        from flash_attn import flash_attn_func
+    except Exception:
+        return {"error": "FlashAttention is not available for comparison"}
+    head_dim = hidden_size // num_heads
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v = (torch.randn(batch_size, seq_len, num_heads, head_dim, device="cuda", dtype=torch.float16, generator=g) for _ in range(3))
+    qr, kr, vr = (t.permute(0, 2, 1, 3) for t in (q, k, v))
+    try:
+        flash = lambda: flash_attn_func(q, k, v, dropout_p=0.0, softmax_scale=1.0 / math.sqrt(head_dim))
+        flash_out = flash()
+        torch.cuda.synchronize()
+    except Exception as e:  # (the package's binaries may not cover this architecture)
+        return {"error": f"FlashAttention is not available for comparison: {type(e).__name__}"}
+    ring_out = triton_ring_attention_forward(qr, kr, vr).reshape(batch_size, seq_len, num_heads, head_dim)
+    t_flash = M.time_ms(flash, 5, 10)
+    t_ring = M.time_ms(lambda: triton_ring_attention_forward(qr, kr, vr), 5, 10)
+    err = (flash_out.float() - ring_out.float()).abs()
+    return {"flash_attention_time_ms": t_flash, "ring_attention_time_ms": t_ring, "flash_vs_ring_speedup": t_ring / t_flash,
+            "max_absolute_diff": err.max().item(), "mean_absolute_diff": err.mean().item(),
+            "relative_error": err.mean().item() / flash_out.float().abs().mean().item()}
+
+
+def calculate_attention_theoretical_flops(seq_len: int, batch_size: int, hidden_size: int, num_heads: int) -> Dict[str, float]:
+    """reference :1735-1800 — the reference's operation-count model (one count per multiply-accumulate; softmax 5 per score
+    in the materialised form, 7 in the chunked form with 128-key chunks; projections included)."""
+    head_dim = hidden_size // num_heads
+    proj = 4 * batch_size * seq_len * hidden_size * hidden_size            # Q, K, V and output projections
+    scores = batch_size * num_heads * seq_len * seq_len                    # entries of the score matrix
+    std_total = proj + 2 * scores * head_dim + 5 * scores
+    chunk = min(128, seq_len)
+    covered = batch_size * num_heads * seq_len * (-(-seq_len // chunk)) * chunk   # keys rounded up to whole chunks
+    ring_total = proj + 2 * covered * head_dim + 7 * covered
+    flash_total = proj + 2 * scores * head_dim
+    return {"standard_attention_gflops": std_total / 1e9, "ring_attention_gflops": ring_total / 1e9,
+            "flash_attention_gflops": flash_total / 1e9, "standard_to_ring_flops_ratio": std_total / ring_total,
+            "ring_to_flash_flops_ratio": ring_total / flash_total}

@@ -7,11 +7,13 @@ through its (batch, seq, head) strides without copies. (The reference fuses both
 run; projection fusion into the attention kernel itself is out of scope, §2.2.)"""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
+import torch.nn.functional as F
 
 from ... import ops
+from .. import _measure as M
 
 HAS_TRITON = True
 
@@ -74,3 +76,72 @@ def ring_compatible_wrapper(hidden_states, layernorm_weight, layernorm_bias, q_w
     q, k, v = triton_fused_layernorm_qkv(hidden_states, layernorm_weight, layernorm_bias, q_weight, k_weight, v_weight,
                                          q_bias, k_bias, v_bias, eps, num_heads, num_kv_heads)
     return q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's own measurement / validation helpers for this file (:707-1060), same arguments and result keys.
+# ------------------------------------------------------------------------------------------------------------------
+def _lnqkv_problem(batch_size, seq_len, hidden_size, num_heads, num_kv_heads, device, dtype=torch.bfloat16):
+    if num_heads == 0:
+        num_heads = max(1, hidden_size // 64)
+    num_kv_heads = num_heads if num_kv_heads is None else num_kv_heads
+    head_dim = hidden_size // num_heads
+    g = torch.Generator(device=device).manual_seed(0)
+    r = lambda *s, sc=1.0: (torch.randn(*s, device=device, generator=g) * sc).to(dtype)
+    sc = hidden_size ** -0.5
+    return (r(batch_size, seq_len, hidden_size), r(hidden_size), r(hidden_size, sc=0.1),
+            r(num_heads * head_dim, hidden_size, sc=sc), r(num_kv_heads * head_dim, hidden_size, sc=sc),
+            r(num_kv_heads * head_dim, hidden_size, sc=sc), r(num_heads * head_dim, sc=0.1), r(num_kv_heads * head_dim, sc=0.1),
+            r(num_kv_heads * head_dim, sc=0.1), num_heads, num_kv_heads)
+
+
+def _unfused_lnqkv(x, lw, lb, wq, wk, wv, bq, bk, bv, fp32: bool):
+    """Comparator: torch LayerNorm followed by three separate library GEMMs."""
+    c = (lambda t: t.float()) if fp32 else (lambda t: t)
+    n = F.layer_norm(c(x), (x.shape[-1],), c(lw), c(lb), 1e-5)
+    return F.linear(n, c(wq), c(bq)), F.linear(n, c(wk), c(bk)), F.linear(n, c(wv), c(bv))
+
+
+def benchmark_fused_layernorm_qkv(batch_size: int, seq_len: int, hidden_size: int, num_heads: int = 0,
+                                  num_kv_heads: Optional[int] = None, device: str = "cuda", iterations: int = 100,
+                                  warmup: int = 10) -> Dict[str, float]:
+    """reference :707-837 — K5 + one K3 GEMM next to torch LayerNorm + three cuBLAS GEMMs."""
+    res = {"batch_size": batch_size, "seq_len": seq_len, "hidden_size": hidden_size, "triton_fused_ms": 0.0,
+           "separate_pytorch_ms": 0.0, "speedup": 0.0}
+    if not M.cuda_ready(device):
+        return res
+    x, lw, lb, wq, wk, wv, bq, bk, bv, H, Hkv = _lnqkv_problem(batch_size, seq_len, hidden_size, num_heads, num_kv_heads, device)
+    res.update(num_heads=H, num_kv_heads=Hkv)
+    res["triton_fused_ms"] = M.time_ms(lambda: triton_fused_layernorm_qkv(x, lw, lb, wq, wk, wv, bq, bk, bv, 1e-5, H, Hkv),
+                                       warmup, iterations)
+    res["separate_pytorch_ms"] = M.time_ms(lambda: _unfused_lnqkv(x, lw, lb, wq, wk, wv, bq, bk, bv, False), warmup, iterations)
+    res["speedup"] = res["separate_pytorch_ms"] / max(res["triton_fused_ms"], 1e-9)
+    return res
+
+
+def compare_with_unfused_implementation(batch_size: int, seq_len: int, hidden_size: int, num_heads: int = 0,
+                                        num_kv_heads: Optional[int] = None, device: str = "cuda") -> Dict[str, float]:
+    """reference :840-948 — per-projection max difference to the unfused fp32 computation."""
+    if not M.cuda_ready(device):
+        return {"max_difference_q": 0.0, "max_difference_k": 0.0, "max_difference_v": 0.0, "is_correct": False}
+    x, lw, lb, wq, wk, wv, bq, bk, bv, H, Hkv = _lnqkv_problem(batch_size, seq_len, hidden_size, num_heads, num_kv_heads, device)
+    q, k, v = triton_fused_layernorm_qkv(x, lw, lb, wq, wk, wv, bq, bk, bv, 1e-5, H, Hkv)
+    rq, rk, rv = _unfused_lnqkv(x, lw, lb, wq, wk, wv, bq, bk, bv, True)
+    B, S = x.shape[:2]
+    dq, dk, dv = (M.max_abs_diff(a.reshape(B, S, -1), b) for a, b in ((q, rq), (k, rk), (v, rv)))
+    tol = 4 * M.MAX_ABS_TOL  # the normalised activations are rounded to bf16 between the two kernels (|LN(x)| up to ~10)
+    return {"max_difference_q": dq, "max_difference_k": dk, "max_difference_v": dv, "is_correct": max(dq, dk, dv) <= tol,
+            "batch_size": batch_size, "seq_len": seq_len, "hidden_size": hidden_size, "num_heads": H, "num_kv_heads": Hkv}
+
+
+def profile_memory_usage(batch_size: int, seq_len: int, hidden_size: int, num_heads: int = 0, num_kv_heads: Optional[int] = None,
+                         device: str = "cuda") -> Dict[str, float]:
+    """reference :951-1060 — peak memory of both forms (here the concatenated weight is built per call, see the module text)."""
+    if not M.cuda_ready(device):
+        return {"unfused_memory_mb": 0.0, "fused_memory_mb": 0.0, "memory_saving_percent": 0.0}
+    x, lw, lb, wq, wk, wv, bq, bk, bv, H, Hkv = _lnqkv_problem(batch_size, seq_len, hidden_size, num_heads, num_kv_heads, device)
+    mem_u, _ = M.peak_mb(lambda: _unfused_lnqkv(x, lw, lb, wq, wk, wv, bq, bk, bv, False))
+    mem_f, _ = M.peak_mb(lambda: triton_fused_layernorm_qkv(x, lw, lb, wq, wk, wv, bq, bk, bv, 1e-5, H, Hkv))
+    return {"unfused_memory_mb": mem_u, "fused_memory_mb": mem_f, "memory_saving_mb": mem_u - mem_f,
+            "memory_saving_percent": 100.0 * (mem_u - mem_f) / max(mem_u, 1e-6), "batch_size": batch_size, "seq_len": seq_len,
+            "hidden_size": hidden_size}

@@ -397,3 +397,44 @@ def test_triton_fused_attention_shim_vs_fp32_reference():
     assert err[valid].max().item() <= 2e-2 * max(1.0, ref.abs().max().item() / 4), err.max().item()
     with pytest.raises(ValueError):
         triton_fused_attention(x, wqkv[:-8], bqkv, wo, bo, num_heads=H)
+
+
+@pytest.mark.gpu
+def test_reference_measurement_helpers_run_and_validate():
+    """The reference's in-module validation / benchmark helpers (see tests/test_host_modules.py for the signatures), run
+    on the GPU at small sizes: every ``is_correct`` must hold and the reported keys are the reference's."""
+    from kernels.attention import ring_attention as ra
+    from kernels.triton import attention_kernels as ak
+    from kernels.triton import flash_attention_kernels as fk
+    from kernels.triton import fused_layernorm_qkv as lq
+    from kernels.triton import layernorm_kernels as ln
+    from kernels.triton import mlp_kernels as mk
+
+    r = fk.compare_with_standard_attention(512, 2, 4, 64)
+    assert r["is_correct"] and r["max_difference"] <= 2e-2 and r["memory_flash_mb"] < r["memory_standard_mb"]
+    r = fk.benchmark_flash_attention(1024, 2, 4, 128, causal=True, iterations=5, warmup=2)
+    assert r["flash_attention_ms"] > 0 and r["pytorch_attention_ms"] > 0 and r["speedup"] > 0
+    assert set(fk.compare_with_xformers(256, 1, 2, 64)) >= {"has_xformers", "flash_attention_ms", "xformers_attention_ms", "speedup_ratio"}
+    for act in ("gelu", "relu", "swiglu"):
+        r = mk.validate_fused_mlp(2, 100, 256, 512, activation=act)
+        assert r["is_correct"], r
+    r = mk.benchmark_fused_mlp(2, 256, 512, 1024, "swiglu", num_warmup=2, num_iter=5)
+    assert r["triton_time_ms"] > 0 and r["pytorch_time_ms"] > 0
+    r = mk.profile_memory_usage(4, 512, 512, 2048, "swiglu")
+    assert r["triton_memory_mb"] > 0 and r["triton_memory_mb"] <= r["pytorch_memory_mb"]   # one [T, i] workspace vs up, gate, product
+    r = ln.compare_with_torch_layernorm(2, 128, 768)
+    assert r["is_correct"] and r["is_residual_correct"], r
+    r = ln.benchmark_layernorm(2, 512, 1024, iterations=5, warmup=2)
+    assert r["triton_layernorm_ms"] > 0 and r["triton_layernorm_residual_ms"] > 0
+    r = ln.profile_memory_usage(4, 512, 1024)
+    assert r["triton_memory_mb"] < r["torch_memory_mb"]                                        # no materialised x + residual
+    r = lq.compare_with_unfused_implementation(2, 128, 512, 8, 2)
+    assert r["is_correct"], r
+    r = lq.benchmark_fused_layernorm_qkv(2, 256, 512, 8, iterations=5, warmup=2)
+    assert r["triton_fused_ms"] > 0 and r["separate_pytorch_ms"] > 0
+    assert set(lq.profile_memory_usage(2, 256, 512, 8)) >= {"unfused_memory_mb", "fused_memory_mb", "memory_saving_percent"}
+    r = ak.compare_with_flash_attention(512, 2, 512, 8)
+    assert "error" in r or (r["max_absolute_diff"] <= 2e-2 and r["ring_attention_time_ms"] > 0)
+    r = ra.compare_with_standard_attention(512, 2, 512, 8)
+    assert r["max_absolute_diff"] <= 2e-2 and r["ring_time_ms"] > 0 and r["standard_time_ms"] > 0
+    assert r["ring_memory_mb"] < r["standard_memory_mb"]

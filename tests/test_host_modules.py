@@ -399,3 +399,62 @@ def test_model_loader_registry_and_random_init():
     assert isinstance(l, TorchModelLoader) and l.get_model_config()["parameters"] == 6
     with pytest.raises(ValueError):
         load_model("x", loader_name="nope", device="cpu")
+
+
+def test_measurement_helpers_mirror_the_reference_signatures_and_result_keys():
+    """The reference ships benchmark_* / compare_with_* / validate_* / profile_memory_usage helpers next to each kernel
+    (flash_attention_kernels.py:1786-2060, attention_kernels.py:1643-1800, mlp_kernels.py:810-1090,
+    layernorm_kernels.py:318-600, fused_layernorm_qkv.py:707-1060, ring_attention.py:838-1040). The mirrors take the same
+    positional arguments and report the same keys; without a GPU they report zeros exactly as the reference's do (a report,
+    not a fallback: nothing is computed)."""
+    from kernels.attention import ring_attention as ra
+    from kernels.triton import attention_kernels as ak
+    from kernels.triton import flash_attention_kernels as fk
+    from kernels.triton import fused_layernorm_qkv as lq
+    from kernels.triton import layernorm_kernels as ln
+    from kernels.triton import mlp_kernels as mk
+
+    want = {
+        fk.benchmark_flash_attention: ["seq_len", "batch_size", "num_heads", "head_dim", "device", "causal", "iterations", "warmup"],
+        fk.compare_with_standard_attention: ["seq_len", "batch_size", "num_heads", "head_dim", "device"],
+        fk.compare_with_xformers: ["seq_len", "batch_size", "num_heads", "head_dim", "device"],
+        ak.compare_with_flash_attention: ["seq_len", "batch_size", "hidden_size", "num_heads"],
+        ak.calculate_attention_theoretical_flops: ["seq_len", "batch_size", "hidden_size", "num_heads"],
+        mk.benchmark_fused_mlp: ["batch_size", "seq_len", "hidden_size", "intermediate_size", "activation", "device", "dtype",
+                                 "num_warmup", "num_iter"],
+        mk.validate_fused_mlp: ["batch_size", "seq_len", "hidden_size", "intermediate_size", "activation", "device", "dtype"],
+        mk.profile_memory_usage: ["batch_size", "seq_len", "hidden_size", "intermediate_size", "activation", "device"],
+        ln.benchmark_layernorm: ["batch_size", "seq_len", "hidden_size", "device", "iterations", "warmup"],
+        ln.compare_with_torch_layernorm: ["batch_size", "seq_len", "hidden_size", "device"],
+        ln.profile_memory_usage: ["batch_size", "seq_len", "hidden_size", "device"],
+        lq.benchmark_fused_layernorm_qkv: ["batch_size", "seq_len", "hidden_size", "num_heads", "num_kv_heads", "device",
+                                           "iterations", "warmup"],
+        lq.compare_with_unfused_implementation: ["batch_size", "seq_len", "hidden_size", "num_heads", "num_kv_heads", "device"],
+        lq.profile_memory_usage: ["batch_size", "seq_len", "hidden_size", "num_heads", "num_kv_heads", "device"],
+        ra.benchmark_ring_attention: ["seq_len", "batch_size", "hidden_size", "num_heads"],
+        ra.compare_with_standard_attention: ["seq_len", "batch_size", "hidden_size", "num_heads"],
+        ra.calculate_theoretical_flops: ["seq_len", "batch_size", "hidden_size", "num_heads"],
+    }
+    for fn, names in want.items():
+        got = list(inspect.signature(fn).parameters)
+        assert got[:len(names)] == names, (fn.__module__, fn.__name__, got)
+    # the reference's operation-count model, values taken from the reference function itself (tests/golden is not needed:
+    # three integers per case)
+    f = ak.calculate_attention_theoretical_flops(4096, 2, 1024, 16)
+    assert f["standard_attention_gflops"] == pytest.approx(105.763569664) and f["ring_attention_gflops"] == pytest.approx(106.837311488)
+    assert f["flash_attention_gflops"] == pytest.approx(103.079215104)
+    f = ak.calculate_attention_theoretical_flops(100, 1, 256, 4)     # ragged last chunk
+    assert f["standard_to_ring_flops_ratio"] == pytest.approx(0.9974695075661724)
+    assert f["ring_to_flash_flops_ratio"] == pytest.approx(1.0089358660130718)
+    if not torch.cuda.is_available():
+        assert fk.benchmark_flash_attention(128, 1, 2, 64) == {
+            "sequence_length": 128, "batch_size": 1, "num_heads": 2, "head_dim": 64, "causal": False, "flash_attention_ms": 0.0,
+            "pytorch_attention_ms": 0.0, "speedup": 0.0}
+        assert fk.compare_with_standard_attention(128, 1, 2, 64)["is_correct"] is False
+        assert mk.validate_fused_mlp(1, 8, 64, 128) == {"is_correct": False, "max_diff": 0.0}
+        assert mk.benchmark_fused_mlp(1, 8, 64, 128)["triton_time_ms"] == 0.0
+        assert ln.compare_with_torch_layernorm(1, 8, 64) == {"max_difference": 0.0, "is_correct": False}
+        assert lq.compare_with_unfused_implementation(1, 8, 64)["is_correct"] is False
+        assert set(ln.profile_memory_usage(1, 8, 64)) == {"torch_memory_mb", "triton_memory_mb", "memory_saving_percent"}
+    with pytest.raises(ValueError, match="Unsupported activation"):
+        mk._mlp_problem(1, 8, 64, 128, "tanh", "cpu", torch.bfloat16)
