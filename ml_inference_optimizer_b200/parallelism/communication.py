@@ -171,9 +171,17 @@ def gather_along_sequence_dim(tensor: torch.Tensor, sp_size: Optional[int] = Non
         return tensor
     parts = [torch.empty_like(tensor) for _ in range(ws)]
     dist.all_gather(parts, tensor.contiguous(), group=group)
+    return merge_sequence_shards(parts, partition)
+
+
+def merge_sequence_shards(parts: Sequence[torch.Tensor], partition: str = "contiguous") -> torch.Tensor:
+    """Inverse of ``scatter_along_sequence_dim`` for a list holding every rank's shard (rank order)."""
     if partition == "contiguous":
-        return torch.cat(parts, dim=1)
-    c = tensor.size(1) // 2
+        return torch.cat(list(parts), dim=1)
+    if partition != "zigzag":
+        raise ValueError(f"unknown partition {partition!r}")
+    ws = len(parts)
+    c = parts[0].size(1) // 2
     chunks = [None] * (2 * ws)
     for r, p in enumerate(parts):
         a, b = zigzag_chunk_ids(r, ws)

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Callable, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -198,6 +198,16 @@ class SequenceShardedModule(nn.Module):
         self.config = config
         self.partition = partition
 
+    def optimize_for_inference(self) -> None:
+        """reference :326-342 — fp32 parameters are cast to the configured 16-bit communication dtype (these kernels compute
+        in 16 bit anyway) and the wrapped module's own hook, if any, is called."""
+        if self.config.communication_dtype in (torch.float16, torch.bfloat16):
+            for p in self.parameters():
+                if p.dtype == torch.float32:
+                    p.data = p.data.to(self.config.communication_dtype)
+        if hasattr(self.module, "optimize_for_inference"):
+            self.module.optimize_for_inference()
+
     def forward(self, hidden_states: torch.Tensor, *args, **kwargs) -> torch.Tensor:
         local = partition_sequence(hidden_states, self.config, self.partition)
         out = self.module(local.contiguous(), *args, **kwargs)
@@ -217,13 +227,74 @@ class SequenceParallelConverter:
         self.partition = partition
 
     def convert_model(self, model: nn.Module) -> nn.Module:
+        """reference :734-755 — a deep copy with attention and MLP layers swapped, wrapped in ``SequenceShardedModule`` (narrow
+        the input to this rank's shard, all-gather the output along the sequence)."""
+        import copy
+
+        converted = self.convert_mlp_layers(self.convert_attention_layers(copy.deepcopy(model)))
+        return SequenceShardedModule(converted, self.config, self.partition)
+
+    def convert_attention_layers(self, model: nn.Module) -> nn.Module:
+        """reference :757-810 — in place; every attention block with four Linears becomes ``SequenceParallelAttention``."""
         for name, sub in list(model.named_children()):
             new = self._convert(sub)
             if new is not None:
                 setattr(model, name, new)
             else:
-                self.convert_model(sub)
+                self.convert_attention_layers(sub)
         return model
+
+    def convert_mlp_layers(self, model: nn.Module) -> nn.Module:
+        """reference :812-878 — in place; two-Linear feed-forward blocks (``fc1/fc2``, ``dense_h_to_4h/dense_4h_to_h``, ``wi/wo``,
+        GPT-2 ``c_fc/c_proj``) become ``SequenceParallelMLP`` with the weights copied and the block's own activation. Gated
+        (three-Linear) blocks are token-wise too and run unchanged on the shard; ``MLPConverter`` fuses those."""
+        for name, sub in list(model.named_children()):
+            new = self._convert_mlp(sub)
+            if new is not None:
+                setattr(model, name, new)
+            else:
+                self.convert_mlp_layers(sub)
+        return model
+
+    def partition_input_data(self, inputs: Dict[str, torch.Tensor]) -> List[Dict[str, torch.Tensor]]:
+        """reference :880-908 — one input dictionary per SP rank: the sequence tensors (``input_ids``, ``attention_mask``,
+        ``token_type_ids``) narrowed to that rank's shard, everything else passed through."""
+        seq_keys = ("input_ids", "attention_mask", "token_type_ids")
+        return [{k: (comm.scatter_along_sequence_dim(v, self.config.sp_size, partition=self.partition, rank=r).contiguous()
+                     if k in seq_keys else v) for k, v in inputs.items()} for r in range(self.config.sp_size)]
+
+    def gather_output_data(self, outputs: List[torch.Tensor]) -> torch.Tensor:
+        """reference :910-920 — inverse of the partition above for a list holding every rank's output."""
+        return comm.merge_sequence_shards(list(outputs), partition=self.partition)
+
+    def _convert_mlp(self, m: nn.Module) -> Optional[nn.Module]:
+        if isinstance(m, (SequenceParallelMLP, SequenceParallelAttention, SequenceShardedModule)):
+            return None
+        if any(hasattr(m, a) for a in ("gate_proj", "fc1_gate", "w3")):
+            return None
+        pair, transposed = None, False
+        for a, b in (("fc1", "fc2"), ("dense_h_to_4h", "dense_4h_to_h"), ("wi", "wo"), ("c_fc", "c_proj")):
+            if hasattr(m, a) and hasattr(m, b):
+                pair = (getattr(m, a), getattr(m, b))
+                transposed = not isinstance(pair[0], nn.Linear)   # GPT-2 Conv1D keeps [in, out]
+                break
+        if pair is None or not all(hasattr(l, "weight") and l.weight.dim() == 2 for l in pair):
+            return None
+        w1 = pair[0].weight.t() if transposed else pair[0].weight
+        w2 = pair[1].weight.t() if transposed else pair[1].weight
+        if w2.shape != (w1.shape[1], w1.shape[0]):
+            return None
+        act = next((getattr(m, a) for a in ("activation_fn", "activation", "act") if callable(getattr(m, a, None))), F.gelu)
+        b1, b2 = getattr(pair[0], "bias", None), getattr(pair[1], "bias", None)
+        new = SequenceParallelMLP(w1.shape[1], w1.shape[0], self.config, activation=act, dropout_prob=0.0,
+                                  bias=b1 is not None and b2 is not None)
+        with torch.no_grad():
+            new.dense_h_to_4h.weight.copy_(w1)
+            new.dense_4h_to_h.weight.copy_(w2)
+            if new.dense_h_to_4h.bias is not None:
+                new.dense_h_to_4h.bias.copy_(b1)
+                new.dense_4h_to_h.bias.copy_(b2)
+        return new.to(device=w1.device, dtype=w1.dtype)
 
     def _convert(self, m: nn.Module) -> Optional[nn.Module]:
         if isinstance(m, SequenceParallelAttention):

@@ -11,8 +11,9 @@ weights (:684-690), the ``num_partitions`` keyword mismatch (:293).
 """
 from __future__ import annotations
 
+import math
 import os
-from typing import Callable, Optional
+from typing import Callable, Dict, Optional
 
 import torch
 import torch.distributed as dist
@@ -79,6 +80,13 @@ def _linear(x, w, b, local_linear=None):
     return ops.linear_act(x, w, b)
 
 
+def _reset_linear_shard(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> None:
+    nn.init.kaiming_uniform_(weight, a=math.sqrt(5))
+    if bias is not None:
+        fan_in = weight.shape[1]
+        nn.init.uniform_(bias, -1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+
+
 class ColumnParallelLinear(nn.Module):
     """reference :88-204 — weight ``[out/tp, in]``; optional all-gather of the output."""
 
@@ -103,6 +111,16 @@ class ColumnParallelLinear(nn.Module):
             self.weight.copy_(weight[r * s:(r + 1) * s])
             if self.bias is not None and bias is not None:
                 self.bias.copy_(bias[r * s:(r + 1) * s])
+
+    def reset_parameters(self):
+        """reference :152-159 — nn.Linear's default initialisation of the shard (Kaiming-uniform weight, fan-in bias)."""
+        _reset_linear_shard(self.weight, self.bias)
+
+    def get_master_weight(self) -> torch.Tensor:
+        """reference :189-204 — the unsharded ``[out, in]`` weight (all-gather of the row blocks over the TP group)."""
+        if self.tp_size == 1:
+            return self.weight
+        return pu.gather_tensor_along_dim(self.weight.detach(), 0, self.config.get_tp_group())
 
     def forward(self, x: torch.Tensor):
         b = None if self.skip_bias_add else self.bias
@@ -136,6 +154,16 @@ class RowParallelLinear(nn.Module):
             self.weight.copy_(weight[:, r * s:(r + 1) * s])
             if self.bias is not None and bias is not None:
                 self.bias.copy_(bias)
+
+    def reset_parameters(self):
+        """reference :271-278."""
+        _reset_linear_shard(self.weight, self.bias)
+
+    def get_master_weight(self) -> torch.Tensor:
+        """reference :312-327 — the unsharded ``[out, in]`` weight (all-gather of the column blocks over the TP group)."""
+        if self.tp_size == 1:
+            return self.weight
+        return pu.gather_tensor_along_dim(self.weight.detach(), 1, self.config.get_tp_group())
 
     def forward(self, x: torch.Tensor):
         if not self.input_is_parallel and self.tp_size > 1:
@@ -333,7 +361,27 @@ class TensorParallelAttention(nn.Module):
         self.value = ColumnParallelLinear(hidden_size, self.num_kv_heads * self.head_dim, config=self.config, gather_output=False)
         self.output = RowParallelLinear(num_attention_heads * self.head_dim, hidden_size, config=self.config, input_is_parallel=True)
         self.dropout = nn.Dropout(attention_dropout)
+        self.communication_schedule_optimized = False
         self._local_attn = None  # test hook
+
+    # reference attribute names of the per-rank head split (:449-451)
+    @property
+    def num_heads_per_partition(self) -> int:
+        return self.heads_per_rank
+
+    @property
+    def attention_head_size(self) -> int:
+        return self.head_dim
+
+    def transpose_for_scores(self, x: torch.Tensor) -> torch.Tensor:
+        """reference :497-509 — ``[B, S, heads_per_rank * D]`` -> ``[B, heads_per_rank, S, D]`` (a view; K1 itself reads the
+        ``[B, S, H, D]`` form through strides, so ``forward`` does not need it)."""
+        return x.view(*x.shape[:-1], -1, self.head_dim).permute(0, 2, 1, 3)
+
+    def optimize_communication_schedule(self, inference_only: bool = True) -> None:
+        """reference :601-614 (a flag there). The one collective of this block is the all-reduce behind the output
+        projection; nothing is left to re-schedule for a single attention call, so this records the request only."""
+        self.communication_schedule_optimized = True
 
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 encoder_hidden_states: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -356,8 +404,27 @@ class ModelParallelConverter:
     """reference :617-798 — swaps ``*.mlp`` blocks made of two Linears (or gate/up/down) for ``TensorParallelMLP``,
     sharding and COPYING the weights."""
 
-    def __init__(self, config: TensorParallelConfig):
-        self.config = config
+    def __init__(self, config: Optional[TensorParallelConfig] = None):
+        self.config = config or TensorParallelConfig()
+
+    def convert_to_column_parallel(self, linear: nn.Linear) -> ColumnParallelLinear:
+        """reference :729-764 — this rank's row block of ``linear`` (weight and bias copied)."""
+        col = ColumnParallelLinear(linear.in_features, linear.out_features, bias=linear.bias is not None, config=self.config)
+        col = col.to(device=linear.weight.device, dtype=linear.weight.dtype)
+        col.load_full(linear.weight.detach(), None if linear.bias is None else linear.bias.detach())
+        return col
+
+    def convert_to_row_parallel(self, linear: nn.Linear) -> RowParallelLinear:
+        """reference :766-798 — this rank's column block of ``linear``; the bias stays whole (added after the all-reduce)."""
+        row = RowParallelLinear(linear.in_features, linear.out_features, bias=linear.bias is not None, config=self.config)
+        row = row.to(device=linear.weight.device, dtype=linear.weight.dtype)
+        row.load_full(linear.weight.detach(), None if linear.bias is None else linear.bias.detach())
+        return row
+
+    def distribute_model(self, model: nn.Module) -> Dict[int, nn.Module]:
+        """reference :800-816 — converts in place; one process per GPU, so every rank of the map is this process's model."""
+        converted = self.convert_model(model)
+        return {rank: converted for rank in range(self.config.world_size)}
 
     def convert_model(self, model: nn.Module) -> nn.Module:
         for name, sub in list(model.named_children()):

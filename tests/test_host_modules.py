@@ -458,3 +458,109 @@ def test_measurement_helpers_mirror_the_reference_signatures_and_result_keys():
         assert set(ln.profile_memory_usage(1, 8, 64)) == {"torch_memory_mb", "triton_memory_mb", "memory_saving_percent"}
     with pytest.raises(ValueError, match="Unsupported activation"):
         mk._mlp_problem(1, 8, 64, 128, "tanh", "cpu", torch.bfloat16)
+
+
+def test_tensor_parallel_linear_and_converter_surface():
+    """reference tensor_parallel.py:152-159/:189-204/:271-327 (reset_parameters, get_master_weight), :497-509
+    (transpose_for_scores), :601-614, :729-816 (convert_to_column/row_parallel, distribute_model) — single process (tp = 1
+    shards are the whole matrix) plus a tp = 4 shard computed for a chosen rank."""
+    from parallelism.tensor_parallel import ColumnParallelLinear, ModelParallelConverter, RowParallelLinear, TensorParallelAttention
+
+    torch.manual_seed(0)
+    lin = nn.Linear(32, 48)
+    conv = ModelParallelConverter()                       # config defaults to a single rank, as in the reference (:622)
+    col, row = conv.convert_to_column_parallel(lin), conv.convert_to_row_parallel(lin)
+    assert isinstance(col, ColumnParallelLinear) and torch.equal(col.weight, lin.weight) and torch.equal(col.bias, lin.bias)
+    assert isinstance(row, RowParallelLinear) and torch.equal(row.weight, lin.weight) and torch.equal(row.bias, lin.bias)
+    assert col.get_master_weight() is col.weight and row.get_master_weight() is row.weight
+    w0 = col.weight.clone()
+    col.reset_parameters()
+    bound = 1 / math.sqrt(32)
+    assert not torch.equal(col.weight, w0) and col.weight.abs().max() <= bound + 1e-6 and col.bias.abs().max() <= bound
+    cfg4 = TensorParallelConfig(world_size=4, tp_size=4)
+    cfg4.tp_rank = lambda: 2                                # pick a rank without a process group
+    conv4 = ModelParallelConverter(cfg4)
+    c4, r4 = conv4.convert_to_column_parallel(lin), conv4.convert_to_row_parallel(lin)
+    assert torch.equal(c4.weight, lin.weight[24:36]) and torch.equal(c4.bias, lin.bias[24:36])
+    assert torch.equal(r4.weight, lin.weight[:, 16:24]) and torch.equal(r4.bias, lin.bias)   # row-parallel bias stays whole
+    attn = TensorParallelAttention(64, 4, TensorParallelConfig())
+    x = torch.randn(2, 5, 64)
+    t = attn.transpose_for_scores(x)
+    assert t.shape == (2, 4, 5, 16) and torch.equal(t[1, 3, 2], x[1, 2, 48:64])
+    assert attn.num_heads_per_partition == 4 and attn.attention_head_size == 16
+    assert attn.communication_schedule_optimized is False
+    attn.optimize_communication_schedule()
+    assert attn.communication_schedule_optimized is True
+    tiny = nn.Sequential(nn.Linear(8, 8))
+    assert set(ModelParallelConverter(TensorParallelConfig(world_size=2, tp_size=1)).distribute_model(tiny)) == {0, 1}
+
+
+def test_parallel_utils_tensor_helpers():
+    """reference parallel_utils.py:217-286, :426-556."""
+    from parallelism import parallel_utils as pu
+
+    t = torch.arange(24.0).view(2, 3, 4)
+    assert torch.equal(pu.split_tensor_into_1d_equal_chunks(t, 1), t.view(-1))
+    assert torch.equal(pu.gather_1d_tensor_chunks(t.view(-1), t.shape, 1), t)
+    chunk = pu.split_tensor_into_1d_equal_chunks(t, 1)
+    chunk[0] = -1
+    assert t.view(-1)[0] == 0                                   # a copy, as in the reference (.clone())
+    p = nn.Parameter(torch.zeros(4, 4))
+    assert pu.get_parallel_tensor_info(p)["is_parallel"] is False
+    pu.set_tensor_model_parallel_attributes(p, True, 0, 1)
+    q = torch.zeros(2)
+    pu.copy_tensor_model_parallel_attributes(q, p)
+    info = pu.get_parallel_tensor_info(q)
+    assert (info["is_parallel"], info["parallel_dim"], info["parallel_stride"], info["shape"]) == (True, 0, 1, q.shape)
+    mask = torch.ones(2, 1, 8, 8)
+    assert pu.create_attention_mask_for_tp(mask, 1) is mask and pu.create_attention_mask_for_tp(None, 4) is None
+    assert pu.create_attention_mask_for_tp(mask, 4).shape == (2, 1, 8, 2)   # (rank 0 without a group: first key block)
+
+
+def test_sequence_parallel_converter_surface():
+    """reference sequence_parallel.py:326-342, :734-920: convert_model = deep copy -> attention layers -> MLP layers -> wrapped in
+    SequenceShardedModule; weights are copied (the reference builds fresh random modules, Appendix B);
+    partition_input_data / gather_output_data are inverses for both partitions."""
+    from parallelism.sequence_parallel import (SequenceParallelAttention, SequenceParallelConverter, SequenceParallelMLP,
+                                               SequenceShardedModule)
+
+    class Attn(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_attention_heads = 4
+            self.q_proj, self.k_proj, self.v_proj, self.o_proj = (nn.Linear(32, 32) for _ in range(4))
+
+    class MLP(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2, self.act = nn.Linear(32, 96), nn.Linear(96, 32), nn.ReLU()
+
+    class Gated(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.gate_proj, self.up_proj, self.down_proj = nn.Linear(32, 96), nn.Linear(32, 96), nn.Linear(96, 32)
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn, self.mlp, self.gated = Attn(), MLP(), Gated()
+
+    torch.manual_seed(0)
+    blk = Block()
+    cfg = SequenceParallelConfig(world_size=1, sp_size=1)
+    out = SequenceParallelConverter(cfg, causal=True).convert_model(blk)
+    assert isinstance(out, SequenceShardedModule) and isinstance(blk.attn, Attn)          # the original is untouched
+    new = out.module
+    assert isinstance(new.attn, SequenceParallelAttention) and torch.equal(new.attn.query.weight, blk.attn.q_proj.weight)
+    assert isinstance(new.mlp, SequenceParallelMLP) and torch.equal(new.mlp.dense_h_to_4h.weight, blk.mlp.fc1.weight)
+    assert torch.equal(new.mlp.dense_4h_to_h.bias, blk.mlp.fc2.bias) and isinstance(new.mlp.activation, nn.ReLU)
+    assert isinstance(new.gated, Gated)                                                   # gated blocks run unchanged on the shard
+    out.config.communication_dtype = torch.bfloat16
+    out.optimize_for_inference()
+    assert all(p.dtype == torch.bfloat16 for p in out.parameters())
+    ids = torch.arange(2 * 16).view(2, 16)
+    for part in ("contiguous", "zigzag"):
+        conv = SequenceParallelConverter(SequenceParallelConfig(world_size=4, sp_size=4), partition=part)
+        parts = conv.partition_input_data({"input_ids": ids, "labels": torch.tensor([1, 2])})
+        assert len(parts) == 4 and all(p["input_ids"].shape == (2, 4) and torch.equal(p["labels"], torch.tensor([1, 2])) for p in parts)
+        assert torch.equal(conv.gather_output_data([p["input_ids"] for p in parts]), ids)
