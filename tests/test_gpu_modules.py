@@ -499,3 +499,65 @@ def test_sequence_and_tensor_parallel_converters_run_the_kernels_single_rank():
         y2 = row(F.relu(col(x)))
         mr, mx = rel(y2, blk.float().mlp(x.float()))
         assert mr < 1e-2 and mx < 3e-2, (mr, mx)
+
+
+@pytest.mark.gpu
+def test_kv_cache_transformer_runner_and_fusion_registry_on_gpu():
+    """Row f1 on the GPU: (1) the plain KVCache feeds K2 directly (contiguous decode == oracle on the appended keys);
+    (2) TransformerInferenceRunner converts the model, owns a PagedKVCache, generates through K1 / kv_append / K2 (twice:
+    the cache is released between requests) and reports the reference's statistics; (3) the fusion registry's fused MLP
+    reproduces the modules it replaced; (4) convert_to_flash_attention."""
+    import torch.nn as nn
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from baseline.inference import KVCache, TransformerInferenceRunner, convert_to_flash_attention, fusion_registry
+    from ml_inference_optimizer_b200 import ops
+
+    torch.manual_seed(0)
+    B, H, Hkv, D, S = 2, 8, 2, 128, 300
+    cache = KVCache(max_batch_size=B, max_seq_len=512, use_block_storage=False)
+    cache.initialize(num_layers=1, num_heads=Hkv, head_dim=D, dtype=torch.bfloat16, device="cuda")
+    k, v = torch.randn(B, S, Hkv, D, device="cuda", dtype=torch.bfloat16), torch.randn(B, S, Hkv, D, device="cuda", dtype=torch.bfloat16)
+    lens = [S, 177]
+    for b in range(B):
+        cache.append(0, b, k[b, :lens[b] - 1], v[b, :lens[b] - 1])
+        cache.append(0, b, k[b, lens[b] - 1:lens[b]], v[b, lens[b] - 1:lens[b]])     # the decode step's own token
+    q = torch.randn(B, H, D, device="cuda", dtype=torch.bfloat16)
+    kc, vc, cl = cache.decode_views(0)
+    o = ops.decode_attention(q, kc, vc, cl)
+    for b in range(B):
+        ref, _ = orc.attention_ref(q[b:b + 1, None].cpu(), k[b:b + 1, :lens[b]].cpu(), v[b:b + 1, :lens[b]].cpu())
+        assert (o[b].float().cpu() - ref[0, 0]).abs().max().item() <= 2e-2
+
+    cfg = GPT2Config(n_layer=2, attn_implementation="eager")
+    model = GPT2LMHeadModel(cfg).eval().to("cuda", torch.bfloat16)
+    ids = torch.randint(0, cfg.vocab_size, (2, 21), device="cuda")
+    ref = model.generate(ids, max_new_tokens=8, do_sample=False, pad_token_id=0)
+    runner = TransformerInferenceRunner(model, "cuda", "bf16", kv_cache_num_gpu_blocks=8, kv_cache_block_size=16)
+    assert (runner.num_layers, runner.num_heads, runner.head_dim) == (2, 12, 64)
+    stats = runner.get_kv_cache_stats()
+    assert stats["kv_cache_enabled"] and stats["kv_cache_type"] == "PagedAttention"
+    for _ in range(2):
+        n0 = ops.launch_count()
+        out, metrics = runner.run_inference({"input_ids": ids}, max_new_tokens=8)
+        assert ops.launch_count() > n0 and "cuda_time_ms" in metrics
+        assert out.shape == ref.shape and (out == ref).float().mean().item() >= 0.9
+        assert runner.paged_kv_cache.block_manager.get_num_free_blocks() == 8          # released after the request
+    logits = runner.run_inference({"input_ids": ids})[0].logits
+    assert (logits.float() - model(ids).logits.float()).abs().max().item() < 0.25
+    with pytest.raises(NotImplementedError, match="greedy"):
+        runner.run_inference({"input_ids": ids}, max_new_tokens=4, do_sample=True)
+
+    seq = nn.Sequential(nn.LayerNorm(256), nn.Linear(256, 512), nn.GELU(), nn.Linear(512, 256)).to("cuda", torch.bfloat16)
+    fused = fusion_registry.fuse_modules(seq)
+    x = torch.randn(3, 100, 256, device="cuda", dtype=torch.bfloat16)
+    n0 = ops.launch_count()
+    y = fused(x)
+    assert ops.launch_count() > n0
+    mr, mx = rel(y, seq.float()(x.float()))
+    assert mr < 1e-2 and mx < 3e-2, (mr, mx)
+
+    conv = convert_to_flash_attention(GPT2LMHeadModel(cfg).eval().to("cuda", torch.bfloat16))
+    assert type(conv.transformer.h[0].attn).__name__ == "_HFAttentionAdapter"
+    with pytest.raises(ValueError, match="no convertible attention"):
+        convert_to_flash_attention(nn.Sequential(nn.Linear(8, 8)).to("cuda", torch.bfloat16))

@@ -564,3 +564,68 @@ def test_sequence_parallel_converter_surface():
         parts = conv.partition_input_data({"input_ids": ids, "labels": torch.tensor([1, 2])})
         assert len(parts) == 4 and all(p["input_ids"].shape == (2, 4) and torch.equal(p["labels"], torch.tensor([1, 2])) for p in parts)
         assert torch.equal(conv.gather_output_data([p["input_ids"] for p in parts]), ids)
+
+
+def test_kv_cache_runner_helpers_and_fusion_registry_cpu():
+    """Row f1, host logic: the plain KVCache (reference baseline/inference.py:791-1043), the runner helpers (:616-784) and the
+    module-pattern fusion registry (:26-281: matching, slot replacement, Sequential renumbering, weights copied)."""
+    from baseline.inference import (BasicInferenceRunner, FusionPattern, FusionRegistry, KVCache, TransformerInferenceRunner,
+                                    fusion_registry)
+    from kernels.mlp.fused_mlp import FusedMLP as _FusedMLP
+
+    c = KVCache(max_batch_size=2, max_seq_len=8, use_block_storage=True, block_size=4)
+    with pytest.raises(RuntimeError, match="not initialized"):
+        c.get_kv_cache(0)
+    assert c.get_memory_usage() == {"total_memory_mb": 0}
+    c.initialize(num_layers=2, num_heads=3, head_dim=4, dtype=torch.float32, device="cpu")
+    assert c.get_kv_cache(0, 1) == (None, None)
+    k, v = torch.randn(5, 3, 4), torch.randn(5, 3, 4)
+    for layer in range(2):                      # the same 5 tokens into both layers: length 5, not 10
+        c.append(layer, 1, k, v)
+    assert c.current_seq_lengths == [0, 5]
+    c.append(0, 1, k[:2], v[:2])
+    gk, gv = c.get_kv_cache(0, 1)
+    assert torch.equal(gk, torch.cat([k, k[:2]])) and torch.equal(gv, torch.cat([v, v[:2]])) and c.current_seq_lengths == [0, 7]
+    with pytest.raises(ValueError, match="exceeds maximum"):
+        c.append(0, 1, k[:2], v[:2])
+    kc, vc, lens = c.decode_views(0)
+    assert kc.shape == (2, 8, 3, 4) and lens.tolist() == [0, 7] and lens.dtype == torch.int32
+    use = c.get_memory_usage()
+    assert use["total_memory_mb"] == pytest.approx(2 * 2 * 2 * 8 * 3 * 4 * 4 / 2 ** 20)
+    assert use["memory_efficiency"] == pytest.approx((2 + 2) / (2 * 2 * 2))   # blocks touched: layer 0 -> 2, layer 1 -> 2, of 8
+    c.reset()
+    assert c.current_seq_lengths == [0, 0] and c.is_initialized
+    c.clear()
+    assert not c.is_initialized and c.k_caches == {}
+
+    runner = BasicInferenceRunner(nn.Linear(4, 4), device="cpu")
+    runner.warmup(torch.randn(2, 4), iterations=2)
+    res = runner.run_batch_inference([torch.randn(2, 4), torch.randn(3, 4)])
+    assert [r[0].shape[0] for r in res] == [2, 3] and runner.last_batch_metrics["avg_inference_time_ms"] > 0
+    assert "model_inference" in runner.profile_model(torch.randn(2, 4), use_cuda=False)["table"]
+    t = TransformerInferenceRunner(nn.Linear(4, 4), device="cpu")      # no CUDA: no cache, plain forward
+    assert t.get_kv_cache_stats() == {"kv_cache_enabled": False} and t.run_inference(torch.randn(2, 4))[0].shape == (2, 4)
+
+    assert [p.name for p in fusion_registry.patterns] == ["linear_gelu_linear", "linear_relu_linear"]
+    seq = nn.Sequential(nn.LayerNorm(16), nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 16), nn.Dropout(0.0))
+    fused = fusion_registry.fuse_modules(seq)
+    assert isinstance(seq[1], nn.Linear) and list(fused._modules) == ["0", "1", "2"]       # copy by default, renumbered
+    assert isinstance(fused[1], _FusedMLP) and fused[1]._activation() == "relu"
+    assert torch.equal(fused[1].fc1.weight, seq[1].weight) and torch.equal(fused[1].fc2.bias, seq[3].bias)
+
+    class Named(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.up, self.act, self.down, self.norm = nn.Linear(16, 32, bias=False), nn.GELU(), nn.Linear(32, 16), nn.LayerNorm(16)
+
+    m = fusion_registry.fuse_modules(Named(), inplace=True)
+    assert isinstance(m.up, _FusedMLP) and m.up._activation() == "gelu_erf" and not hasattr(m, "act") and not hasattr(m, "down")
+    assert torch.count_nonzero(m.up.fc1.bias) == 0                                       # a missing bias becomes zeros
+    assert fusion_registry.fuse_modules(nn.Sequential(nn.Linear(16, 32), nn.GELU(approximate="tanh"), nn.Linear(32, 16)))[0]._activation() == "gelu_tanh"
+    with pytest.raises(ValueError, match="hidden -> intermediate -> hidden"):
+        fusion_registry.fuse_modules(nn.Sequential(nn.Linear(16, 32), nn.ReLU(), nn.Linear(32, 8)))
+    reg = FusionRegistry()
+    assert reg.fuse_modules(seq) is not seq and reg.find_matching_pattern([seq[0]]) is None
+    reg.register_pattern(FusionPattern("ln_linear", [nn.LayerNorm, nn.Linear], lambda mods: nn.Sequential(*mods)))
+    assert reg.patterns[0].description == "Fuses LayerNorm + Linear" and reg.patterns[0].match([seq[0], seq[1]])
+    assert isinstance(reg.fuse_modules(seq)[0], nn.Sequential)
