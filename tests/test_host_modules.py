@@ -629,3 +629,45 @@ def test_kv_cache_runner_helpers_and_fusion_registry_cpu():
     reg.register_pattern(FusionPattern("ln_linear", [nn.LayerNorm, nn.Linear], lambda mods: nn.Sequential(*mods)))
     assert reg.patterns[0].description == "Fuses LayerNorm + Linear" and reg.patterns[0].match([seq[0], seq[1]])
     assert isinstance(reg.fuse_modules(seq)[0], nn.Sequential)
+
+
+def test_model_utils_inspection_helpers():
+    """reference baseline/model_utils.py:18-260, :455-598."""
+    from baseline import model_utils as mu
+
+    class Attn(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj, self.k_proj, self.v_proj = nn.Linear(8, 8), nn.Linear(8, 8), nn.Linear(8, 8)
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.self_attn = Attn()
+            self.mlp = nn.Sequential(nn.Linear(8, 16), nn.GELU(), nn.Linear(16, 8))
+            self.drop = nn.Dropout(0.1)
+
+    m = Block()
+    size = mu.get_model_size(m)
+    n = 3 * (8 * 8 + 8) + (8 * 16 + 16) + (16 * 8 + 8)
+    assert size["total_params"] == size["trainable_params"] == n and size["param_bytes_per_element"] == 4
+    assert size["param_memory_mb"] == pytest.approx(n * 4 / 2 ** 20) and size["param_dtype"] == "torch.float32"
+    assert mu.get_attention_modules(m) == [m.self_attn]
+    assert mu.get_mlp_modules(m) == [m.mlp, m.mlp[0], m.mlp[1], m.mlp[2]]   # "mlp" in the module path: the block and its children
+    layers = mu.get_model_layers(m)
+    assert m.self_attn.q_proj in layers and m.mlp not in layers and m.drop not in layers and m.self_attn not in layers
+    assert [name for name, _ in mu.find_modules_by_type(m, nn.Linear)] == ["self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj",
+                                                                          "mlp.0", "mlp.2"]
+    assert next(mu.convert_precision(m, "bf16").parameters()).dtype == torch.bfloat16
+    with pytest.raises(ValueError, match="Unsupported precision"):
+        mu.convert_precision(m, "int3")
+    assert mu.create_random_input(2, 3, 4, device="cpu").shape == (2, 3, 4)
+    mu.freeze_layers(m, ["self_attn.*", "mlp.2.bias"])
+    frozen = sorted(name for name, p in m.named_parameters() if not p.requires_grad)
+    assert len(frozen) == 7 and "mlp.2.bias" in frozen and "mlp.0.weight" not in frozen
+    m = m.float()
+    sd = {"mlp.0.weight": torch.ones(16, 8), "mlp.2.weight": torch.ones(3, 3), "nope": torch.zeros(1)}
+    res = mu.load_partial_weights(m, sd)
+    assert torch.equal(m.mlp[0].weight, torch.ones(16, 8)) and "mlp.2.weight" not in res.unexpected_keys
+    with pytest.raises(RuntimeError, match="Shape-mismatched keys"):
+        mu.load_partial_weights(m, sd, strict=True)
