@@ -284,7 +284,9 @@ class SequenceParallelConverter:
         w2 = pair[1].weight.t() if transposed else pair[1].weight
         if w2.shape != (w1.shape[1], w1.shape[0]):
             return None
-        act = next((getattr(m, a) for a in ("activation_fn", "activation", "act") if callable(getattr(m, a, None))), F.gelu)
+        from ..kernels.mlp.fused_mlp import MLPConverter, resolve_activation
+        act = MLPConverter._module_activation(m)
+        resolve_activation(act)   # strict: a block without an activation attribute, or with one that has no fused epilogue, raises
         b1, b2 = getattr(pair[0], "bias", None), getattr(pair[1], "bias", None)
         new = SequenceParallelMLP(w1.shape[1], w1.shape[0], self.config, activation=act, dropout_prob=0.0,
                                   bias=b1 is not None and b2 is not None)

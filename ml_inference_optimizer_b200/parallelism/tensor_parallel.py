@@ -445,10 +445,14 @@ class ModelParallelConverter:
             return TensorParallelMLP.from_dense(m.up_proj.weight, m.up_proj.bias, m.down_proj.weight, m.down_proj.bias,
                                                 self.config, F.silu, m.gate_proj.weight, m.gate_proj.bias)
         if hasattr(m, "fc1") and hasattr(m, "fc2") and isinstance(m.fc1, nn.Linear):
-            act = getattr(m, "activation_fn", getattr(m, "act", F.gelu))
+            from ..kernels.mlp.fused_mlp import MLPConverter
+            act = MLPConverter._module_activation(m)
+            activation_name(act)   # strict: no activation attribute / no fused epilogue raises instead of assuming GELU
             return TensorParallelMLP.from_dense(m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self.config, act)
         if hasattr(m, "c_fc") and hasattr(m, "c_proj"):  # GPT-2 Conv1D, weight [in, out]
-            act = getattr(m, "act", F.gelu)
+            from ..kernels.mlp.fused_mlp import MLPConverter
+            act = MLPConverter._module_activation(m)
+            activation_name(act)
             return TensorParallelMLP.from_dense(m.c_fc.weight.t().contiguous(), m.c_fc.bias, m.c_proj.weight.t().contiguous(),
                                                 m.c_proj.bias, self.config, act)
         return None

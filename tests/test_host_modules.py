@@ -558,6 +558,16 @@ def test_sequence_parallel_converter_surface():
     out.config.communication_dtype = torch.bfloat16
     out.optimize_for_inference()
     assert all(p.dtype == torch.bfloat16 for p in out.parameters())
+    class NoAct(nn.Module):                      # a two-Linear block that does not say what sits between them: refused, not guessed
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = nn.Linear(32, 96), nn.Linear(96, 32)
+
+    with pytest.raises(ValueError, match="no activation attribute"):
+        SequenceParallelConverter(cfg).convert_mlp_layers(nn.Sequential(NoAct()))
+    with pytest.raises(ValueError, match="no activation attribute"):
+        from parallelism.tensor_parallel import ModelParallelConverter
+        ModelParallelConverter().convert_model(nn.Sequential(NoAct()))
     ids = torch.arange(2 * 16).view(2, 16)
     for part in ("contiguous", "zigzag"):
         conv = SequenceParallelConverter(SequenceParallelConfig(world_size=4, sp_size=4), partition=part)
