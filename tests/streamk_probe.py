@@ -1,4 +1,5 @@
-"""Developer probe (B200 via gpurun): decode-sized linear layers and the T=64 FusedMLP replayed from CUDA graphs of 10 calls,
+"""Developer probe (B200 via gpurun; needs tests/experiments/r2_stream_k_skinny_gemm.patch applied — without it the
+variants all run the shipped kernel): decode-sized linear layers and the T=64 FusedMLP replayed from CUDA graphs of 10 calls,
 stream-K on / off and the producer's issue batch (B200_GEMM_STREAMK, B200_GEMM_ISSUE_BATCH, read per call = at capture time), next to cuBLAS."""
 import json
 import os
