@@ -173,6 +173,7 @@ class SequenceParallelMLP(nn.Module):
         self.dropout = nn.Dropout(dropout_prob)
         self.sp_group = config.get_sp_group()
         self.sp_rank, self.dp_rank = config.get_rank_info()
+        self._local_mlp = None  # test hook (CPU/gloo host-logic tests)
         nn.init.xavier_uniform_(self.dense_h_to_4h.weight)
         nn.init.xavier_uniform_(self.dense_4h_to_h.weight)
         if bias:
@@ -184,6 +185,9 @@ class SequenceParallelMLP(nn.Module):
         from .. import ops
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("dropout is not implemented (inference path)")
+        if self._local_mlp is not None:
+            return self._local_mlp(hidden_states, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight,
+                                   self.dense_4h_to_h.bias, activation_name(self.activation))
         return ops.fused_mlp(hidden_states, self.dense_h_to_4h.weight, self.dense_h_to_4h.bias, self.dense_4h_to_h.weight,
                              self.dense_4h_to_h.bias, activation_name(self.activation))
 

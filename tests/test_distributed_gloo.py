@@ -168,7 +168,69 @@ def _sp_attention_module_case(rank, world):
     return out
 
 
+def _sp_converter_case(rank, world):
+    """SequenceParallelConverter.convert_model end to end: deep copy -> attention + MLP swapped (weights copied) -> wrapped in
+    SequenceShardedModule, which narrows the full input to this rank's shard and all-gathers the output."""
+    import torch.nn as nn
+
+    from parallelism.sequence_parallel import (SequenceParallelAttention, SequenceParallelConfig, SequenceParallelConverter,
+                                               SequenceParallelMLP)
+
+    H, hid = 4, 32
+
+    class Attn(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_attention_heads = H
+            self.q_proj, self.k_proj, self.v_proj, self.o_proj = (nn.Linear(hid, hid) for _ in range(4))
+
+        def forward(self, x):
+            B, S, _ = x.shape
+            q, k, v = (l(x).view(B, S, H, hid // H) for l in (self.q_proj, self.k_proj, self.v_proj))
+            ctx, _ = orc.attention_ref(q, k, v, causal=True)
+            return self.o_proj(ctx.reshape(B, S, hid))
+
+    class MLP(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2, self.act = nn.Linear(hid, 64), nn.Linear(64, hid), nn.ReLU()
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn, self.mlp = Attn(), MLP()
+
+        def forward(self, x):
+            x = x + self.attn(x)
+            return x + self.mlp(x)
+
+    torch.manual_seed(11)            # the same weights and input on every rank
+    blk = Block().eval()
+    x = torch.randn(2, 16 * world, hid)
+    out = {}
+    for part in ("contiguous", "zigzag"):
+        cfg = SequenceParallelConfig(world_size=world, sp_size=world, attention_handling="ring", overlap_communication=False)
+        sp = SequenceParallelConverter(cfg, causal=True, partition=part).convert_model(blk)
+        assert isinstance(sp.module.attn, SequenceParallelAttention) and isinstance(sp.module.mlp, SequenceParallelMLP)
+        sp.module.attn.backend = OracleRingBackend()
+        sp.module.mlp._local_mlp = lambda t, w1, b1, w2, b2, act: orc.mlp_ref(t, w1, b1, w2, b2, act)
+        with torch.no_grad():
+            out[part] = float((sp(x) - blk(x)).abs().max())
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- tests
+@pytest.mark.parametrize("world", [2, 4])
+def test_sequence_parallel_converter_end_to_end(world):
+    for errs in _spawn("_sp_converter_case", world):
+        for key, val in errs.items():
+            assert val < 1e-4, (key, val)
+
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_ring_attention_exact(world):
     for errs in _spawn("_ring_case", world):
