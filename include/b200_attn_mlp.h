@@ -95,7 +95,8 @@ const char* b200_last_kernel(void);
  *   D contiguous; D = any multiple of 8 up to 128 (the reference takes hidden_size // num_heads as it comes,
  *   flash_attention.py:176; kernels are built for 64 and 128 columns, a narrower head runs in the next wider build with
  *   the missing columns zero-filled by the TMA loads and never stored); pointers 16-byte aligned and strides multiples
- *   of 8 elements. (The decode kernels and the paged cache take D in {64, 128} only.)
+ *   of 8 elements. (The decode kernels and the caches take D in {64, 128}; the Python layer stores narrower heads in the
+ *   next wider cache with zero columns behind them.)
  *   lse: fp32 [B,Hq,Sq] contiguous, may be NULL.                                                          */
 int b200_fa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Sq, int Sk, int Hq,
                 int Hkv, int D, const int64_t q_strides[3], const int64_t k_strides[3], const int64_t v_strides[3],

@@ -37,7 +37,10 @@ class BlockManager:
         self.num_heads, self.head_dim, self.dtype, self.device = num_heads, head_dim, dtype, device
         self.free_blocks = list(range(num_blocks))
         self.ref_counts = [0] * num_blocks  # host-side (the reference keeps them on the device and syncs on every access)
-        shape = (num_blocks, num_layers, block_size, num_heads, head_dim)
+        from .. import ops
+        # physical width: 64 or 128 columns (what K2 / kv_append are built for); a narrower head leaves zero columns behind it
+        self.physical_head_dim = ops.cache_head_dim(head_dim)
+        shape = (num_blocks, num_layers, block_size, num_heads, self.physical_head_dim)
         self.gpu_cache_k = torch.zeros(shape, dtype=dtype, device=device)
         self.gpu_cache_v = torch.zeros(shape, dtype=dtype, device=device)
         self.is_initialized = True
@@ -181,8 +184,8 @@ class PagedKVCache:
             table = torch.tensor(self.get_block_table(sid), dtype=torch.long)
             blk = table[pos // self.block_size].to(k.device)
             off = (pos % self.block_size).to(k.device)
-            kc[blk, layer_idx, off] = k[b].to(kc.dtype)
-            vc[blk, layer_idx, off] = v[b].to(vc.dtype)
+            kc[blk, layer_idx, off, :, :k.shape[-1]] = k[b].to(kc.dtype)   # (columns past head_dim stay zero)
+            vc[blk, layer_idx, off, :, :v.shape[-1]] = v[b].to(vc.dtype)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -318,7 +321,8 @@ class KVCache:
     def initialize(self, num_layers: int, num_heads: int, head_dim: int, dtype: torch.dtype = torch.float16,
                    device: str = "cuda") -> None:
         self.num_layers, self.num_heads, self.head_dim = num_layers, num_heads, head_dim
-        shape = (self.max_batch_size, self.max_seq_len, num_heads, head_dim)
+        from .. import ops
+        shape = (self.max_batch_size, self.max_seq_len, num_heads, ops.cache_head_dim(head_dim))   # zero columns past head_dim
         self.k_caches = {l: torch.zeros(shape, dtype=dtype, device=device) for l in range(num_layers)}
         self.v_caches = {l: torch.zeros(shape, dtype=dtype, device=device) for l in range(num_layers)}
         self._lengths = [[0] * self.max_batch_size for _ in range(num_layers)]
@@ -346,7 +350,7 @@ class KVCache:
         n = self._lengths[layer_idx][batch_idx]
         if n == 0 and self.use_block_storage:
             return None, None
-        return self.k_caches[layer_idx][batch_idx, :n], self.v_caches[layer_idx][batch_idx, :n]
+        return self.k_caches[layer_idx][batch_idx, :n, :, :self.head_dim], self.v_caches[layer_idx][batch_idx, :n, :, :self.head_dim]
 
     def append(self, layer_idx: int, batch_idx: int, k: torch.Tensor, v: torch.Tensor) -> None:
         """k, v ``[seq_len, num_heads, head_dim]`` appended behind what the layer already holds."""
@@ -355,8 +359,8 @@ class KVCache:
         new = cur + k.size(0)
         if new > self.max_seq_len:
             raise ValueError(f"Sequence length {new} exceeds maximum {self.max_seq_len}")
-        self.k_caches[layer_idx][batch_idx, cur:new] = k
-        self.v_caches[layer_idx][batch_idx, cur:new] = v
+        self.k_caches[layer_idx][batch_idx, cur:new, :, :self.head_dim] = k
+        self.v_caches[layer_idx][batch_idx, cur:new, :, :self.head_dim] = v
         self._lengths[layer_idx][batch_idx] = new
 
     def decode_views(self, layer_idx: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -66,6 +66,19 @@ def _last_dim_contiguous(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(-1) == 1 else t.contiguous()
 
 
+def cache_head_dim(head_dim: int) -> int:
+    """Head width a KV cache is allocated with: the decode kernels and ``kv_append`` are built for 64 and 128 columns, so a
+    narrower head (any multiple of 8) is stored in the next wider cache with zero columns behind it — exact, the zeros add
+    nothing to a score and produce zero outputs. q / k / v narrower than the cache are padded on the fly by the ops below."""
+    if head_dim <= 0 or head_dim % 8 != 0 or head_dim > 128:
+        raise ValueError(f"head_dim {head_dim} unsupported (a multiple of 8, at most 128)")
+    return 64 if head_dim <= 64 else 128
+
+
+def _pad_head(t: torch.Tensor, width: int) -> torch.Tensor:
+    return t if t.shape[-1] == width else torch.nn.functional.pad(t, (0, width - t.shape[-1]))
+
+
 # --------------------------------------------------------------------------------------------------------
 # K1 prefill attention
 # --------------------------------------------------------------------------------------------------------
@@ -155,8 +168,17 @@ def paged_prefill_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: tor
         raise ValueError("expected q [B,Sq,Hq,D] and caches [num_blocks, L, block_size, Hkv, D]")
     B, Sq, Hq, D = q.shape
     num_blocks, num_layers, block_size, Hkv, Dk = k_cache.shape
-    if Dk != D or k_cache.dtype != q.dtype or v_cache.dtype != q.dtype:
+    if Dk < D or k_cache.dtype != q.dtype or v_cache.dtype != q.dtype:
         raise ValueError("cache head_dim / dtype must match q")
+    if Dk != D:   # a narrower head stored in a wider cache (cache_head_dim): zero columns behind q, the caller's scale
+        scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+        res = paged_prefill_attention(_pad_head(q, Dk), k_cache, v_cache, block_tables, context_lens, layer_idx, causal, scale,
+                                      return_lse)
+        o = (res[0] if return_lse else res)[..., :D]
+        if out is not None:
+            out.copy_(o)
+            o = out
+        return (o, res[1]) if return_lse else o
     if not k_cache.is_contiguous() or not v_cache.is_contiguous():
         raise ValueError("paged cache must be contiguous")
     if block_tables.dtype != torch.int32 or block_tables.dim() != 2 or block_tables.shape[0] != B or not block_tables.is_contiguous():
@@ -271,8 +293,17 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
         kv_bs, kv_ts = k_cache.stride(0), k_cache.stride(1)
         num_layers, block_size, max_blocks = 1, 0, 0
         layout = KV_CONTIGUOUS
-    if Dk != D:
+    if Dk < D:
         raise ValueError("head_dim of q and cache differ")
+    if Dk != D:   # a narrower head stored in a wider cache (cache_head_dim)
+        scale = float(softmax_scale) if softmax_scale is not None else 1.0 / math.sqrt(D)
+        res = decode_attention(_pad_head(q, Dk), k_cache, v_cache, context_lens, scale, block_tables, layer_idx, max_context_len,
+                               num_splits, return_lse)
+        o = (res[0] if return_lse else res)[..., :D]
+        if out is not None:
+            out.copy_(o)
+            o = out
+        return (o, res[1]) if return_lse else o
     if max_context_len is None:
         max_context_len = cap
     max_context_len = int(min(max_context_len, cap))
@@ -325,8 +356,10 @@ def kv_append(key: torch.Tensor, value: torch.Tensor, k_cache: torch.Tensor, v_c
         Hc, Dc = k_cache.shape[2], k_cache.shape[3]
         kv_bs, kv_ts = k_cache.stride(0), k_cache.stride(1)
         num_layers, block_size, max_blocks = 1, 0, k_cache.shape[1]  # contiguous: the capacity S_max travels in max_blocks
-    if (Hc, Dc) != (Hkv, D):
+    if Hc != Hkv or Dc < D:
         raise ValueError(f"cache heads / head_dim {(Hc, Dc)} do not match key {(Hkv, D)}")
+    if Dc != D:   # a narrower head stored in a wider cache (cache_head_dim): zero columns behind the new token's K, V
+        key, value, D = _pad_head(key, Dc), _pad_head(value, Dc), Dc
     lib = _lib.load()
     with torch.cuda.device(dev):
         rc = lib.b200_kv_append(key.data_ptr(), value.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), B, Hkv, D,

@@ -561,3 +561,24 @@ def test_kv_cache_transformer_runner_and_fusion_registry_on_gpu():
     assert type(conv.transformer.h[0].attn).__name__ == "_HFAttentionAdapter"
     with pytest.raises(ValueError, match="no convertible attention"):
         convert_to_flash_attention(nn.Sequential(nn.Linear(8, 8)).to("cuda", torch.bfloat16))
+
+
+@pytest.mark.gpu
+def test_paged_generation_with_head_dim_96():
+    """A model whose head_dim (96) has no dedicated kernel build: prefill through K1 (TMA zero-fill), the paged cache stored
+    128 wide, decode / kv_append on padded tokens — greedy generation agrees with the HF cache path."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    from baseline.inference import TransformerInferenceRunner
+
+    torch.manual_seed(0)
+    cfg = GPT2Config(n_layer=2, n_head=4, n_embd=384, attn_implementation="eager")
+    model = GPT2LMHeadModel(cfg).eval().to("cuda", torch.bfloat16)
+    ids = torch.randint(0, cfg.vocab_size, (2, 19), device="cuda")
+    ref = model.generate(ids, max_new_tokens=8, do_sample=False, pad_token_id=0)
+    runner = TransformerInferenceRunner(model, "cuda", "bf16", kv_cache_num_gpu_blocks=8)
+    assert runner.head_dim == 96 and runner.paged_kv_cache.get_physical_caches()[0].shape[-1] == 128
+    for graph in (False, True):
+        runner.use_cuda_graph = graph
+        out, _ = runner.run_inference({"input_ids": ids}, max_new_tokens=8)
+        assert out.shape == ref.shape and (out == ref).float().mean().item() >= 0.9, graph

@@ -368,6 +368,54 @@ def test_decode_paged_and_kv_append(ops):
     check_lse(lse, rl)
 
 
+@pytest.mark.parametrize("D", [32, 80, 96])
+def test_paged_cache_with_narrow_heads(ops, D):
+    """Head dims the decode kernels are not built for live in the next wider cache (ops.cache_head_dim) with zero columns
+    behind them: kv_append writes the padded token bit-exactly, decode and short-q attention on the narrow q equal the oracle
+    on the narrow tensors, with the softmax scale of the REAL head_dim."""
+    g = torch.Generator(device="cuda").manual_seed(D)
+    Dp = ops.cache_head_dim(D)
+    assert Dp == (64 if D <= 64 else 128)
+    B, Hq, Hkv, bs, L, nblk = 2, 8, 2, 16, 2, 40
+    r = lambda *shape: torch.randn(*shape, device="cuda", dtype=torch.bfloat16, generator=g)
+    kc, vc = torch.zeros(nblk, L, bs, Hkv, Dp, device="cuda", dtype=torch.bfloat16), torch.zeros(nblk, L, bs, Hkv, Dp, device="cuda", dtype=torch.bfloat16)
+    kc[..., :D], vc[..., :D] = r(nblk, L, bs, Hkv, D), r(nblk, L, bs, Hkv, D)
+    lens = torch.tensor([37, 250], device="cuda", dtype=torch.int32)
+    tables = torch.randperm(nblk)[:B * 16].view(B, 16).to(device="cuda", dtype=torch.int32)
+    key, val = r(B, Hkv, D), r(B, Hkv, D)
+    ops.kv_append(key, val, kc, vc, lens, block_tables=tables, layer_idx=1)
+    rk, rv = kc[..., :D].cpu().clone(), vc[..., :D].cpu().clone()        # narrow reference cache, after the append
+    for b in range(B):
+        pos = int(lens[b]) - 1
+        blk = int(tables[b, pos // bs])
+        assert torch.equal(kc[blk, 1, pos % bs, :, :D], key[b]) and kc[blk, 1, pos % bs, :, D:].abs().sum() == 0
+        assert torch.equal(vc[blk, 1, pos % bs, :, :D], val[b])
+    q = r(B, Hq, D)
+    o, lse = ops.decode_attention(q, kc, vc, lens, block_tables=tables, layer_idx=1, return_lse=True)
+    assert o.shape == (B, Hq, D)
+    ro, rl = orc.decode_attention_ref(q.cpu(), rk, rv, lens.cpu(), block_tables=tables.cpu(), layer_idx=1)
+    check_out(o, ro)
+    check_lse(lse, rl)
+    Sq = 24
+    q4 = r(B, Sq, Hq, D)
+    o4 = ops.paged_prefill_attention(q4, kc, vc, tables, lens, layer_idx=1, causal=True)
+    assert o4.shape == (B, Sq, Hq, D)
+    for b in range(B):
+        n = int(lens[b])
+        idx = torch.arange(n)
+        kb = rk[tables[b].cpu().long()[idx // bs], 1, idx % bs][None]
+        vb = rv[tables[b].cpu().long()[idx // bs], 1, idx % bs][None]
+        ref, _ = orc.attention_ref(q4[b:b + 1].cpu(), kb, vb, causal=True, causal_offset=n - Sq)
+        check_out(o4[b:b + 1], ref)
+    # contiguous cache, same rule
+    kcc, vcc = torch.zeros(B, 300, Hkv, Dp, device="cuda", dtype=torch.bfloat16), torch.zeros(B, 300, Hkv, Dp, device="cuda", dtype=torch.bfloat16)
+    kn, vn = r(B, 300, Hkv, D), r(B, 300, Hkv, D)
+    kcc[..., :D], vcc[..., :D] = kn, vn
+    oc = ops.decode_attention(q, kcc, vcc, lens)
+    roc, _ = orc.decode_attention_ref(q.cpu(), kn.cpu(), vn.cpu(), lens.cpu())
+    check_out(oc, roc)
+
+
 @pytest.mark.parametrize("Sq,Hq,Hkv,D,block_size,causal", [
     (64, 8, 8, 128, 16, True),      # the reference's BLOCK_SIZE_M = 64 case
     (200, 8, 2, 128, 16, True),     # GQA, q tile pair partly empty, ragged context lengths

@@ -280,7 +280,13 @@ def test_paged_kv_cache_bookkeeping():
 
     c = PagedKVCache(num_blocks=6, block_size=4, num_layers=2, num_heads=2, head_dim=8, dtype=torch.float32, device="cpu")
     k, v = c.get_physical_caches()
-    assert k.shape == (6, 2, 4, 2, 8)  # [num_blocks, L, block_size, Hkv, D] (reference baseline/inference.py:1077-1084)
+    # [num_blocks, L, block_size, Hkv, D] (reference baseline/inference.py:1077-1084); D is the PHYSICAL width: 64 or 128
+    # columns (what the decode kernels are built for), a narrower head leaves zero columns behind it
+    assert k.shape == (6, 2, 4, 2, 64) and c.head_dim == 8 and c.block_manager.physical_head_dim == 64
+    assert PagedKVCache(2, 4, 1, 2, 128, dtype=torch.float32, device="cpu").get_physical_caches()[0].shape == (2, 1, 4, 2, 128)
+    assert PagedKVCache(2, 4, 1, 2, 96, dtype=torch.float32, device="cpu").get_physical_caches()[0].shape == (2, 1, 4, 2, 128)
+    with pytest.raises(ValueError, match="head_dim"):
+        PagedKVCache(2, 4, 1, 2, 136, dtype=torch.float32, device="cpu")
     c.allocate_blocks_for_sequence(0, 6)
     assert len(c.get_block_table(0)) == 2 and c.get_sequence_length(0) == 6
     for _ in range(3):
@@ -298,7 +304,8 @@ def test_paged_kv_cache_bookkeeping():
     kk = torch.arange(1 * 4 * 2 * 8, dtype=torch.float32).view(1, 4, 2, 8)
     c.write_prefill(1, [1], kk, kk + 1)
     blk = c.get_block_table(1)[0]
-    assert torch.equal(k[blk, 1], kk[0]) and torch.equal(v[blk, 1], kk[0] + 1) and k[blk, 0].abs().sum() == 0
+    assert torch.equal(k[blk, 1, ..., :8], kk[0]) and torch.equal(v[blk, 1, ..., :8], kk[0] + 1) and k[blk, 0].abs().sum() == 0
+    assert k[blk, 1, ..., 8:].abs().sum() == 0 and v[blk, 1, ..., 8:].abs().sum() == 0      # the padding columns stay zero
     bm = BlockManager(2, 4, 1, 1, 8, torch.float32, "cpu")
     b0 = bm.allocate_block()
     bm.increase_ref_count(b0)
@@ -587,9 +594,9 @@ def test_kv_cache_runner_helpers_and_fusion_registry_cpu():
     with pytest.raises(RuntimeError, match="not initialized"):
         c.get_kv_cache(0)
     assert c.get_memory_usage() == {"total_memory_mb": 0}
-    c.initialize(num_layers=2, num_heads=3, head_dim=4, dtype=torch.float32, device="cpu")
+    c.initialize(num_layers=2, num_heads=3, head_dim=8, dtype=torch.float32, device="cpu")
     assert c.get_kv_cache(0, 1) == (None, None)
-    k, v = torch.randn(5, 3, 4), torch.randn(5, 3, 4)
+    k, v = torch.randn(5, 3, 8), torch.randn(5, 3, 8)
     for layer in range(2):                      # the same 5 tokens into both layers: length 5, not 10
         c.append(layer, 1, k, v)
     assert c.current_seq_lengths == [0, 5]
@@ -599,9 +606,10 @@ def test_kv_cache_runner_helpers_and_fusion_registry_cpu():
     with pytest.raises(ValueError, match="exceeds maximum"):
         c.append(0, 1, k[:2], v[:2])
     kc, vc, lens = c.decode_views(0)
-    assert kc.shape == (2, 8, 3, 4) and lens.tolist() == [0, 7] and lens.dtype == torch.int32
+    assert kc.shape == (2, 8, 3, 64) and lens.tolist() == [0, 7] and lens.dtype == torch.int32   # physical width 64: zero columns past head_dim
+    assert kc[..., 8:].abs().sum() == 0
     use = c.get_memory_usage()
-    assert use["total_memory_mb"] == pytest.approx(2 * 2 * 2 * 8 * 3 * 4 * 4 / 2 ** 20)
+    assert use["total_memory_mb"] == pytest.approx(2 * 2 * 2 * 8 * 3 * 64 * 4 / 2 ** 20)
     assert use["memory_efficiency"] == pytest.approx((2 + 2) / (2 * 2 * 2))   # blocks touched: layer 0 -> 2, layer 1 -> 2, of 8
     c.reset()
     assert c.current_seq_lengths == [0, 0] and c.is_initialized
