@@ -204,6 +204,7 @@ class RingExchange:
         self.use_side_stream = use_side_stream
         self._works = None
         self._event = None
+        self.trace = None   # measurement hook: a list that receives one (start_event, end_event) pair per hop (side stream)
 
     def start(self, send: Sequence[torch.Tensor], recv: Sequence[torch.Tensor]) -> None:
         if self.world == 1:
@@ -233,6 +234,10 @@ class RingExchange:
             import contextlib
             ctx = contextlib.nullcontext()
         with ctx:
+            t0 = None
+            if self.trace is not None and cuda and self.use_side_stream:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(self.stream)
             ops_ = []
             for s, r in zip(send, recv):
                 ops_.append(dist.P2POp(dist.isend, s, nxt, group=self.group))
@@ -241,8 +246,10 @@ class RingExchange:
             if cuda and self.use_side_stream:
                 for w in self._works:
                     w.wait()  # enqueues the completion on the side stream; does not block the host for NCCL
-                self._event = torch.cuda.Event()
+                self._event = torch.cuda.Event(enable_timing=t0 is not None)
                 self._event.record(self.stream)
+                if t0 is not None:
+                    self.trace.append((t0, self._event))
 
     def wait(self) -> None:
         if self.world == 1 or self._works is None:

@@ -73,7 +73,7 @@ class _Acc:
         return self.backend.finalize(self.o, dtype), self.lse
 
 
-def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap, return_lse, n, r):
+def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap, return_lse, n, r, trace=None):
     """Ring with the merge fused into the attention kernel (``backend.attn_accum``): one launch per step, one fp32
     accumulator for all local query rows, no 16-bit partial outputs, no separate merge / slice / concatenate kernels.
     Step 0 is always the rank's own block (src == r), which touches every local query row, so it initialises the
@@ -84,6 +84,9 @@ def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap,
     kv = [torch.stack([k, v]).contiguous(), None]
     kv[1] = torch.empty_like(kv[0])
     exchange = RingExchange(group, use_side_stream=overlap)
+    if trace is not None:   # measurement hook (tests/ring_timeline.py): CUDA events around every kernel and every hop
+        exchange.trace = trace.setdefault("hops", [])
+        trace["attn"] = []
     o_acc = torch.empty(B, S, Hq, D, dtype=torch.float32, device=q.device)
     lse_acc = torch.empty(B, Hq, S, dtype=torch.float32, device=q.device)
     for step in range(n):
@@ -93,6 +96,9 @@ def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap,
         src = (r - step) % n
         kc, vc = cur[0], cur[1]
         init = step == 0
+        if trace is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), src)
+            ev[0].record()
         if not causal:
             backend.attn_accum(q, kc, vc, o_acc, lse_acc, init, False, softmax_scale)
         elif src == r:
@@ -104,6 +110,9 @@ def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap,
                 backend.attn_accum(q[:, half:], kc, vc, o_acc[:, half:], lse_acc[:, :, half:], init, False, softmax_scale)
         elif src < r:     # causal, contiguous shards: earlier ranks are fully visible, later ranks not at all
             backend.attn_accum(q, kc, vc, o_acc, lse_acc, init, False, softmax_scale)
+        if trace is not None:
+            ev[1].record()
+            trace["attn"].append(ev)
         if step + 1 < n:
             exchange.wait()
     out = backend.finalize(o_acc, q.dtype)
@@ -112,7 +121,7 @@ def _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap,
 
 def ring_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False,
                            softmax_scale: Optional[float] = None, group=None, partition: str = "contiguous",
-                           backend=None, overlap: bool = True, return_lse: bool = False):
+                           backend=None, overlap: bool = True, return_lse: bool = False, trace: Optional[dict] = None):
     """q ``[B,S_local,Hq,D]``, k/v ``[B,S_local,Hkv,D]`` — this rank's shard under ``partition``. Returns the local
     output shard ``[B,S_local,Hq,D]`` (and LSE ``[B,Hq,S_local]``)."""
     if partition not in ("contiguous", "zigzag"):
@@ -131,7 +140,7 @@ def ring_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, ca
         raise ValueError("the zigzag partition needs an even local sequence length")
     half = S // 2
     if hasattr(backend, "attn_accum"):
-        return _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap, return_lse, n, r)
+        return _ring_fused(backend, q, k, v, causal, softmax_scale, group, zigzag, overlap, return_lse, n, r, trace)
 
     # KV double buffer: cur is attended to while nxt is being received
     kv = [torch.stack([k, v]).contiguous(), None]
