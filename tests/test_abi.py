@@ -29,6 +29,13 @@ def test_header_cites_reference_interfaces():
         assert cite in header
 
 
+def test_integration_notes_place_every_symbol():
+    header = open(os.path.join(ROOT, "include", "b200_attn_mlp.h")).read()
+    notes = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))) if s not in notes]
+    assert not missing, f"INTEGRATION.md does not say where these entry points bind: {missing}"
+
+
 def test_version_and_pure_host_queries(built_lib):
     assert b"sm_100a" in built_lib.b200_version()
     # wide problem: no split-K; the intermediate + the single-launch kernel's counters (2 per 256-row block + 1, 256-aligned)
