@@ -799,6 +799,12 @@ def run_ours(args, w):
             "gpu_launches": int(launches),
             "gpu_launches_note": "counted by the library (b200_launch_count) inside the timed region, this rank",
             "clocks": clocks,
+            # the other halves of BASELINE.json's metric ("% B200 bf16 peak; prefill tok/s at 1-8 GPU"): the same timed
+            # region expressed as tokens through the layer step per second (whole job) and as fractions of the dense bf16 peak
+            "prefill_tokens_per_s": T / (ms_per_step * 1e-3),
+            "pct_of_bf16_peak": {"measured_burst": 100.0 * value / (n * peaks["tflops_burst"]),
+                                 "measured_sustained": 100.0 * value / (n * peaks["tflops_sustained"]),
+                                 "nominal_2250": 100.0 * value / (n * 2250.0), "peak_source": peaks["source"]},
         }
         if n == 1:
             gemm1_flops = (4.0 if act == "swiglu" else 2.0) * T * h * i
