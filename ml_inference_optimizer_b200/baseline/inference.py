@@ -472,6 +472,9 @@ class TransformerInferenceRunner(InferenceRunner):
         if new_tokens is not None and self.paged_kv_cache is not None:
             if set(kwargs) - {"do_sample"} or kwargs.get("do_sample"):
                 raise NotImplementedError("the paged generation loop is greedy: unsupported arguments " + ", ".join(sorted(kwargs)))
+            mask = inputs.get("attention_mask") if isinstance(inputs, dict) else None
+            if mask is not None and bool((mask == 0).any()):
+                raise NotImplementedError("the paged generation loop serves equal-length, unpadded prompts (attention_mask has zeros)")
             cache = self.paged_kv_cache
             try:
                 return generate_paged(self.model, ids, new_tokens, cache=cache, block_size=self.kv_cache_block_size,

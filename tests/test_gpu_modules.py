@@ -547,6 +547,11 @@ def test_kv_cache_transformer_runner_and_fusion_registry_on_gpu():
     assert (logits.float() - model(ids).logits.float()).abs().max().item() < 0.25
     with pytest.raises(NotImplementedError, match="greedy"):
         runner.run_inference({"input_ids": ids}, max_new_tokens=4, do_sample=True)
+    padded = torch.ones_like(ids)
+    padded[1, :3] = 0
+    with pytest.raises(NotImplementedError, match="unpadded"):
+        runner.run_inference({"input_ids": ids, "attention_mask": padded}, max_new_tokens=4)
+    assert runner.run_inference({"input_ids": ids, "attention_mask": torch.ones_like(ids)}, max_new_tokens=2)[0].shape == (2, 23)
 
     seq = nn.Sequential(nn.LayerNorm(256), nn.Linear(256, 512), nn.GELU(), nn.Linear(512, 256)).to("cuda", torch.bfloat16)
     fused = fusion_registry.fuse_modules(seq)
